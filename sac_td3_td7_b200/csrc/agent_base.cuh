@@ -1,0 +1,210 @@
+// agent_base.cuh -- state shared by the TD7 / TD3 / SAC update engines: parameter blobs,
+// activation arena, step counters, info ring, fork/join streams and CUDA-graph replay.
+#pragma once
+#include "nets.cuh"
+#include "replay.cuh"
+
+namespace b200rl {
+
+constexpr int kInfoRing = 1024;  // update steps whose losses stay readable without a sync
+
+// Gaussian fill: z ~ N(0,1) from Philox(seed; counter = *step_counter, index), unless *inject != 0
+// (then the buffer already holds caller-provided noise -- parity tests).
+__global__ void __launch_bounds__(256) gauss_fill_kernel(float* __restrict__ out_base, long long gs, long long n, unsigned long long seed0, int stream_id,
+                                                         const int* __restrict__ step_counter, const int* __restrict__ inject) {
+  if (*inject) return;
+  const long long pair = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair * 2 >= n) return;
+  // every stacked seed draws from its own key, so its stream equals that of a single-seed run
+  float* out = out_base + (long long)blockIdx.y * gs;
+  Philox ph(seed0 + 0x9E3779B97F4A7C15ULL * (unsigned long long)blockIdx.y);
+  uint32_t r[4];
+  ph(((unsigned long long)(unsigned)(*step_counter) << 8) | (unsigned)stream_id, (unsigned long long)pair, r);
+  float z0, z1;
+  gauss2_from_bits(r[0], r[1], &z0, &z1);
+  out[pair * 2] = z0;
+  if (pair * 2 + 1 < n) out[pair * 2 + 1] = z1;
+}
+
+// copy a caller batch (five [B,.] tensors) into the engine's fixed input buffers
+struct StageArgs {
+  const float* state; const float* action; const float* reward; const float* next_state; const float* done;
+  float* ss; float* act; float* rew; float* nd;
+  int B, S, A;
+};
+__global__ void __launch_bounds__(256) stage_batch_kernel(StageArgs a) {
+  const int nS = a.B * a.S, nA = a.B * a.A;
+  const int total = 2 * nS + nA + 2 * a.B;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    if (i < nS) a.ss[i] = a.state[i];
+    else if (i < 2 * nS) a.ss[i] = a.next_state[i - nS];
+    else if (i < 2 * nS + nA) a.act[i - 2 * nS] = a.action[i - 2 * nS];
+    else if (i < 2 * nS + nA + a.B) a.rew[i - 2 * nS - nA] = a.reward[i - 2 * nS - nA];
+    else a.nd[i - 2 * nS - nA - a.B] = a.done[i - 2 * nS - nA - a.B];
+  }
+}
+
+struct AgentBase {
+  int S = 0, A = 0, H = 256, Z = 256, B = 256, G = 1;
+  bool use_lap = false;
+  bool keep_grads = false;
+  DeviceArena arena;
+  cudaStream_t stream = nullptr;  // capture / setup stream (owned)
+  cudaStream_t exec = nullptr;    // caller's stream: graphs are launched and loose ops enqueued here
+  Fork fork;
+
+  StepState* d_step = nullptr;
+  AdamScalars* d_adam = nullptr;
+  OptimHyper* d_hyper = nullptr;
+  int* d_flags = nullptr;  // [0] = noise injected by caller
+  int nopt = 0;
+  float* d_info = nullptr;
+  int info_cols = 0;
+  long long n_calls = 0;  // host mirror of StepState.n_runs
+  unsigned long long rng_seed = 0xB200B200ULL;
+
+  // activation arena (two-pass layout)
+  float* act_base = nullptr;
+  long long act_cursor = 0, act_stride = 0;
+
+  // fixed input buffers
+  Mat ss, act_in, rew, nd;
+  Replay* bound = nullptr;
+  bool built = false;
+  int launches[4] = {0, 0, 0, 0};  // kernels per update, by graph variant
+#ifndef B200_EMU
+  cudaGraphExec_t graphs[4] = {nullptr, nullptr, nullptr, nullptr};
+#endif
+
+  virtual ~AgentBase() {
+#ifndef B200_EMU
+    for (auto& g : graphs)
+      if (g) cudaGraphExecDestroy(g);
+#endif
+    fork.destroy();
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  Mat alloc_act(int rows, int cols) {
+    Mat m;
+    m.rows = rows; m.cols = cols; m.ld = cols;
+    m.p = act_base ? act_base + act_cursor : nullptr;
+    m.gs = act_stride;
+    act_cursor += round_up((long long)rows * cols, 4);
+    return m;
+  }
+
+  int init_common(int nopt_, int info_cols_, const OptimHyper* hyper) {
+    nopt = nopt_;
+    info_cols = info_cols_;
+    B200_CHECK_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    B200_TRY(fork.init(stream, 3, 64));
+    B200_TRY(arena.alloc(&d_step, 1));
+    B200_TRY(arena.alloc(&d_adam, (size_t)nopt));
+    B200_TRY(arena.alloc(&d_hyper, (size_t)nopt));
+    B200_TRY(arena.alloc(&d_flags, 4));
+    B200_TRY(arena.alloc(&d_info, (size_t)G * kInfoRing * info_cols));
+    B200_CHECK_CUDA(cudaMemcpy(d_hyper, hyper, nopt * sizeof(OptimHyper), cudaMemcpyHostToDevice));
+    return kOk;
+  }
+
+  int alloc_net(Net* n, const NetLayout& L, bool trained, const AdamScalars* adam) {
+    n->L = L;
+    n->gs = L.numel;
+    B200_TRY(arena.alloc(&n->p, (size_t)G * L.numel));
+    if (trained) {
+      B200_TRY(arena.alloc(&n->m, (size_t)G * L.numel));
+      B200_TRY(arena.alloc(&n->v, (size_t)G * L.numel));
+      if (keep_grads) B200_TRY(arena.alloc(&n->grad, (size_t)G * L.numel));
+      n->adam = adam;
+    }
+    return kOk;
+  }
+
+  int copy_net(Net& dst, const Net& src, cudaStream_t s) {
+    B200_CHECK_CUDA(cudaMemcpyAsync(dst.p, src.p, (size_t)G * src.L.numel * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return kOk;
+  }
+
+  int launch_prep(unsigned step_mask, cudaStream_t s) {
+    B200_LAUNCH(prep_step_kernel, dim3(1), dim3(32), 0, s, d_step, d_adam, d_hyper, nopt, step_mask, kInfoRing);
+    B200_CHECK_LAUNCH();
+    return kOk;
+  }
+
+  int launch_gauss(const Mat& noise, int stream_id, cudaStream_t s) {
+    const long long n = (long long)noise.rows * noise.cols;
+    dim3 grid((unsigned)((n / 2 + 256) / 256), (unsigned)G), block(256);
+    B200_LAUNCH(gauss_fill_kernel, grid, block, 0, s, noise.p, noise.gs, n, rng_seed, stream_id, &d_step->n_runs, d_flags);
+    B200_CHECK_LAUNCH();
+    return kOk;
+  }
+
+  // caller-provided batch -> fixed buffers (device pointers, single seed)
+  int stage_batch(const float* state, const float* action, const float* reward, const float* next_state, const float* done, int group) {
+    StageArgs a;
+    const long long o = (long long)group * act_stride;
+    a.state = state; a.action = action; a.reward = reward; a.next_state = next_state; a.done = done;
+    a.ss = ss.p + o; a.act = act_in.p + o; a.rew = rew.p + o; a.nd = nd.p + o;
+    a.B = B; a.S = S; a.A = A;
+    B200_LAUNCH(stage_batch_kernel, dim3(32), dim3(256), 0, exec, a);
+    B200_CHECK_LAUNCH();
+    return kOk;
+  }
+
+  Replay::Outputs replay_outputs() const {
+    Replay::Outputs o;
+    o.state = ss.p; o.ld_state = S; o.state_gs = act_stride;
+    o.next_state = ss.p + (long long)B * S; o.ld_next = S; o.next_gs = act_stride;
+    o.action = act_in.p; o.ld_action = A; o.action_gs = act_stride;
+    o.reward = rew.p; o.reward_gs = act_stride;
+    o.done = nd.p; o.done_gs = act_stride;
+    return o;
+  }
+
+  // ---- graph replay -----------------------------------------------------------------------
+  virtual int issue_step(int variant) = 0;  // enqueue one update on `stream` (+ side streams)
+
+  int run_step(int variant) {
+#ifdef B200_EMU
+    fork.begin_step();
+    const int c0 = launch_counter();
+    const int st_emu = issue_step(variant);
+    launches[variant] = launch_counter() - c0;
+    return st_emu;
+#else
+    if (!graphs[variant] && exec == stream) { set_last_error("agent: the caller stream must differ from the capture stream"); return kErrState; }
+    if (!graphs[variant]) {
+      cudaGraph_t g = nullptr;
+      fork.begin_step();
+      B200_CHECK_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+      const int c0 = launch_counter();
+      int st = issue_step(variant);
+      launches[variant] = launch_counter() - c0;
+      cudaError_t e = cudaStreamEndCapture(stream, &g);
+      if (st != kOk) { if (g) cudaGraphDestroy(g); return st; }
+      B200_CHECK_CUDA(e);
+      B200_CHECK_CUDA(cudaGraphInstantiate(&graphs[variant], g, 0));
+      cudaGraphDestroy(g);
+    }
+    B200_CHECK_CUDA(cudaGraphLaunch(graphs[variant], exec));
+    return kOk;
+#endif
+  }
+  void drop_graphs() {
+#ifndef B200_EMU
+    for (auto& g : graphs) { if (g) cudaGraphExecDestroy(g); g = nullptr; }
+#endif
+  }
+
+  int sync() {
+    B200_CHECK_CUDA(cudaStreamSynchronize(stream));
+    return kOk;
+  }
+  int sync_exec() {
+    B200_CHECK_CUDA(cudaStreamSynchronize(exec));
+    return kOk;
+  }
+};
+
+}  // namespace b200rl

@@ -1,0 +1,156 @@
+// common.cuh -- shared device/host helpers for the b200rl kernels (sm_100a).
+//
+// The same sources are compiled two ways:
+//   * nvcc -gencode arch=compute_100a,code=sm_100a      -> libb200rl.so   (the product)
+//   * g++  -DB200_EMU -include tests/cuemu/cuemu.h      -> test-only CPU emulation of
+//     the kernels' control flow (see tests/cuemu/cuemu.h; never loaded by the package)
+#pragma once
+
+#ifndef B200_EMU
+#include <cuda_runtime.h>
+#define B200_DYN_SMEM(type, name)                            \
+  extern __shared__ __align__(16) unsigned char _dyn_smem[]; \
+  type* name = reinterpret_cast<type*>(_dyn_smem)
+#endif
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+namespace b200rl {
+// kernels launched by this thread since the counter was last reset (bench.py: gpu_launches)
+inline int& launch_counter() {
+  static thread_local int c = 0;
+  return c;
+}
+}  // namespace b200rl
+
+#ifdef B200_EMU
+#undef B200_LAUNCH
+#define B200_LAUNCH(kernel, grid, block, smem, stream, ...)                        \
+  do {                                                                             \
+    ++b200rl::launch_counter();                                                    \
+    cuemu::launch((grid), (block), (smem), [=]() { kernel(__VA_ARGS__); });        \
+  } while (0)
+#else
+#define B200_LAUNCH(kernel, grid, block, smem, stream, ...)            \
+  do {                                                                 \
+    ++b200rl::launch_counter();                                        \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);        \
+  } while (0)
+#endif
+
+namespace b200rl {
+
+// ----------------------------------------------------------------------------- errors
+enum Status : int {
+  kOk = 0,
+  kErrInvalidArg = -1,
+  kErrCuda = -2,
+  kErrNoDevice = -3,
+  kErrState = -4,
+  kErrUnsupported = -5,
+};
+
+void set_last_error(const std::string& msg);
+
+#define B200_CHECK_CUDA(expr)                                                                       \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      b200rl::set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + \
+                             ":" + std::to_string(__LINE__));                                       \
+      return b200rl::kErrCuda;                                                                      \
+    }                                                                                               \
+  } while (0)
+
+#define B200_CHECK_LAUNCH() B200_CHECK_CUDA(cudaGetLastError())
+
+#define B200_REQUIRE(cond, msg)                                        \
+  do {                                                                 \
+    if (!(cond)) {                                                     \
+      b200rl::set_last_error(std::string("invalid argument: ") + msg); \
+      return b200rl::kErrInvalidArg;                                   \
+    }                                                                  \
+  } while (0)
+
+#define B200_TRY(expr)           \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != b200rl::kOk) return _s; \
+  } while (0)
+
+// ----------------------------------------------------------------------------- warp helpers
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// inclusive scan across the 32 lanes of a warp (double)
+__device__ __forceinline__ double warp_inclusive_scan(double v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double n = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += n;
+  }
+  return v;
+}
+
+// ----------------------------------------------------------------------------- Philox4x32-10
+// Counter-based generator (Salmon et al. 2011).  Used for on-device uniforms (replay
+// sampling) and Gaussians (target smoothing / SAC reparameterisation) in the burst path;
+// parity tests inject the draws instead.
+struct Philox {
+  uint32_t key0, key1;
+  __host__ __device__ Philox(uint64_t seed) : key0((uint32_t)seed), key1((uint32_t)(seed >> 32)) {}
+  __host__ __device__ static inline uint32_t mulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+  __host__ __device__ inline void operator()(uint64_t ctr_lo, uint64_t ctr_hi, uint32_t out[4]) const {
+    uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = (uint32_t)ctr_hi, c3 = (uint32_t)(ctr_hi >> 32);
+    uint32_t k0 = key0, k1 = key1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+      uint32_t hi0 = mulhi(M0, c0), lo0 = M0 * c0;
+      uint32_t hi1 = mulhi(M1, c2), lo1 = M1 * c2;
+      uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+  }
+};
+// 24-bit uniform in [0, 1 - 2^-24] (never 1.0, same grid as torch.rand float32)
+__host__ __device__ inline float u01_from_bits(uint32_t b) { return (float)(b >> 8) * (1.0f / 16777216.0f); }
+// Box-Muller from two 32-bit words; u1 in (0,1]
+__device__ inline void gauss2_from_bits(uint32_t b0, uint32_t b1, float* z0, float* z1) {
+  float u1 = ((float)(b0 >> 8) + 1.0f) * (1.0f / 16777216.0f);
+  float u2 = (float)(b1 >> 8) * (1.0f / 16777216.0f);
+  float rad = sqrtf(-2.0f * logf(u1));
+  float s, c;
+  sincosf(6.283185307179586f * u2, &s, &c);
+  *z0 = rad * c;
+  *z1 = rad * s;
+}
+
+// ----------------------------------------------------------------------------- small utils
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline long round_up(long a, long b) { return (a + b - 1) / b * b; }
+
+}  // namespace b200rl

@@ -1,0 +1,171 @@
+// host.cuh -- host-side plumbing: error string, device buffers, launch tables, launchers.
+#pragma once
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm.cuh"
+#include "ops.cuh"
+
+namespace b200rl {
+
+inline std::string& last_error_ref() {
+  static thread_local std::string s;
+  return s;
+}
+inline void set_last_error(const std::string& msg) { last_error_ref() = msg; }
+
+// ----------------------------------------------------------------------------- device memory
+// All persistent state of a handle lives in a few arenas; nothing is allocated on the hot path.
+struct DeviceArena {
+  std::vector<void*> blocks;
+  size_t total_bytes = 0;
+  ~DeviceArena() { release(); }
+  void release() {
+    for (void* b : blocks) cudaFree(b);
+    blocks.clear();
+    total_bytes = 0;
+  }
+  // 256-byte aligned (cudaMalloc alignment); zero-filled
+  template <class T>
+  int alloc(T** out, size_t count) {
+    void* p = nullptr;
+    size_t bytes = count * sizeof(T);
+    if (bytes == 0) bytes = sizeof(T);
+    B200_CHECK_CUDA(cudaMalloc(&p, bytes));
+    B200_CHECK_CUDA(cudaMemset(p, 0, bytes));
+    blocks.push_back(p);
+    total_bytes += bytes;
+    *out = reinterpret_cast<T*>(p);
+    return kOk;
+  }
+};
+
+// ----------------------------------------------------------------------------- gemm tables
+inline GemmProblem make_problem(int I, int J, float* C, int c_ld, long long c_gs = 0) {
+  GemmProblem p;
+  memset(&p, 0, sizeof(p));
+  p.I = I;
+  p.J = J;
+  p.C = C;
+  p.c_ld = c_ld;
+  p.c_gs = c_gs;
+  return p;
+}
+inline void add_seg(GemmProblem& p, const float* A, int a_ld, long long a_gs, const float* B, int b_ld, long long b_gs, int len) {
+  GemmSeg& s = p.seg[p.nseg++];
+  s.A = A; s.a_ld = a_ld; s.a_gs = a_gs;
+  s.B = B; s.b_ld = b_ld; s.b_gs = b_gs;
+  s.len = len;
+  s.b_ones = 0;
+}
+
+inline int gemm_table_upload(GemmTable* t, int mode, std::vector<GemmProblem>& probs, DeviceArena* arena) {
+  int tiles = 0;
+  for (auto& p : probs) {
+    B200_REQUIRE(p.nseg >= 1 && p.nseg <= 3, "gemm problem needs 1..3 segments");
+    B200_REQUIRE(p.I > 0 && p.J > 0, "gemm problem with empty output");
+    p.tile_begin = tiles;
+    p.tiles_j = ceil_div(p.J, kTile);
+    tiles += ceil_div(p.I, kTile) * p.tiles_j;
+  }
+  t->mode = mode;
+  t->nprob = (int)probs.size();
+  t->total_tiles = tiles;
+  B200_TRY(arena->alloc(&t->d_probs, probs.size()));
+  B200_CHECK_CUDA(cudaMemcpy(t->d_probs, probs.data(), probs.size() * sizeof(GemmProblem), cudaMemcpyHostToDevice));
+  return kOk;
+}
+
+inline int gemm_table_launch(const GemmTable& t, int groups, cudaStream_t stream) {
+  if (t.nprob == 0) return kOk;
+  dim3 grid((unsigned)t.total_tiles, (unsigned)groups, 1), block(kGemmThreads, 1, 1);
+  switch (t.mode) {
+    case kFwd: { auto k = gemm_kernel<kFwd>; B200_LAUNCH(k, grid, block, 0, stream, t.d_probs, t.nprob); break; }
+    case kDgrad: { auto k = gemm_kernel<kDgrad>; B200_LAUNCH(k, grid, block, 0, stream, t.d_probs, t.nprob); break; }
+    default: { auto k = gemm_kernel<kWgrad>; B200_LAUNCH(k, grid, block, 0, stream, t.d_probs, t.nprob); break; }
+  }
+  B200_CHECK_LAUNCH();
+  return kOk;
+}
+
+// ----------------------------------------------------------------------------- row-op tables (AvgL1Norm)
+struct RowTable {
+  RowOp* d_ops = nullptr;
+  int nops = 0;
+  int total_rows = 0;
+  bool bwd = false;
+};
+inline RowOp make_rowop(const float* x, int x_ld, long long x_gs, float* y, int y_ld, long long y_gs, int rows, int n,
+                        const float* dy = nullptr, int dy_ld = 0, long long dy_gs = 0) {
+  RowOp r;
+  memset(&r, 0, sizeof(r));
+  r.x = x; r.x_ld = x_ld; r.x_gs = x_gs;
+  r.y = y; r.y_ld = y_ld; r.y_gs = y_gs;
+  r.dy = dy; r.dy_ld = dy_ld; r.dy_gs = dy_gs;
+  r.rows = rows; r.n = n;
+  return r;
+}
+inline int row_table_upload(RowTable* t, bool bwd, std::vector<RowOp>& ops, DeviceArena* arena) {
+  int rows = 0;
+  for (auto& o : ops) { o.row_begin = rows; rows += o.rows; }
+  t->bwd = bwd;
+  t->nops = (int)ops.size();
+  t->total_rows = rows;
+  B200_TRY(arena->alloc(&t->d_ops, ops.size()));
+  B200_CHECK_CUDA(cudaMemcpy(t->d_ops, ops.data(), ops.size() * sizeof(RowOp), cudaMemcpyHostToDevice));
+  return kOk;
+}
+inline int row_table_launch(const RowTable& t, int groups, cudaStream_t stream) {
+  if (t.nops == 0) return kOk;
+  dim3 grid((unsigned)ceil_div(t.total_rows, 8), (unsigned)groups, 1), block(256, 1, 1);
+  if (t.bwd) { auto k = avgl1norm_kernel<true>; B200_LAUNCH(k, grid, block, 0, stream, t.d_ops, t.nops, t.total_rows); }
+  else { auto k = avgl1norm_kernel<false>; B200_LAUNCH(k, grid, block, 0, stream, t.d_ops, t.nops, t.total_rows); }
+  B200_CHECK_LAUNCH();
+  return kOk;
+}
+
+inline int launch_elementwise_grid(long long n) {
+  long long b = (n + 255) / 256;
+  if (b < 1) b = 1;
+  if (b > 148 * 8) b = 148 * 8;
+  return (int)b;
+}
+
+// ----------------------------------------------------------------------------- streams for fork/join
+// Inside a captured graph, parallel branches are expressed with event record/wait between a few
+// side streams; under emulation they degenerate to sequential execution in issue order.
+struct Fork {
+  cudaStream_t main = nullptr;
+  std::vector<cudaStream_t> side;
+  std::vector<cudaEvent_t> events;
+  size_t next_event = 0;
+  int init(cudaStream_t main_stream, int nside, int nevents) {
+    main = main_stream;
+    side.resize(nside);
+    for (auto& s : side) B200_CHECK_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    events.resize(nevents);
+    for (auto& e : events) B200_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return kOk;
+  }
+  void destroy() {
+    for (auto& s : side) cudaStreamDestroy(s);
+    for (auto& e : events) cudaEventDestroy(e);
+    side.clear();
+    events.clear();
+  }
+  void begin_step() { next_event = 0; }
+  // make `to` wait for everything issued so far on `from`
+  int link(cudaStream_t from, cudaStream_t to) {
+    if (next_event >= events.size()) {
+      set_last_error("Fork: out of events");
+      return kErrState;
+    }
+    cudaEvent_t e = events[next_event++];
+    B200_CHECK_CUDA(cudaEventRecord(e, from));
+    B200_CHECK_CUDA(cudaStreamWaitEvent(to, e, 0));
+    return kOk;
+  }
+};
+
+}  // namespace b200rl

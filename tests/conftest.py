@@ -27,3 +27,14 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(scope="session", params=["emu", pytest.param("cuda", marks=pytest.mark.gpu)])
+def dev(request):
+    """C-ABI driver: 'cuda' = the product library on a GPU (parity proper); 'emu' = host emulation
+    of the same kernel sources (logic pre-check in the GPU-less container)."""
+    import devlib
+
+    d = devlib.Dev(request.param)
+    yield d
+    d.free_all()

@@ -1,0 +1,145 @@
+"""Replay kernels through the C ABI vs the oracle and the reference-recorded golden vectors.
+
+Bit-exact: sampled indices, gathered rows, priority scatter, running max, ring cursor.
+"""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+from oracle import replay as oreplay
+
+S, A = 11, 3  # Hopper-v4
+
+
+def _fill(dev, h, n, seed=3, group=0):
+    rows = oreplay.synthetic_rows(n, S, A, seed)
+    packed = dev.pack_rows(h, rows["state"], rows["action"], rows["reward"], rows["next_state"], rows["done"])
+    dev.replay_append(h, packed, group)
+    return rows
+
+
+def test_lap_sampling_matches_reference_golden(dev):
+    g = gu.load("replay_cases")
+    cap = 3000
+    h = dev.replay_create(cap, S, A)
+    rows = _fill(dev, h, cap)
+    for nm in ("ones", "rand", "zeros_mixed", "pow"):
+        for size in (cap, 1777, 1):
+            key = f"samp/{nm}/{size}"
+            pri, u, ind = g[key + "/priority"], g[key + "/u"], g[key + "/ind"]
+            dev.replay_write_priority(h, pri)
+            dev.check(dev.lib.b200rl_replay_set_cursor(h, 0, size % cap, size))
+            idx, batch, _ = dev.replay_sample(h, 256, S, A, u=u)
+            assert np.array_equal(idx[0], ind), key
+            assert np.array_equal(batch["state"][0], rows["state"][ind]), key
+            assert np.array_equal(batch["next_state"][0], rows["next_state"][ind]), key
+            assert np.array_equal(batch["action"][0], rows["action"][ind]), key
+            assert np.array_equal(batch["reward"][0], rows["reward"][ind]), key
+            assert np.array_equal(batch["done"][0], rows["done"][ind]), key
+    dev.check(dev.lib.b200rl_replay_destroy(h))
+
+
+def test_uniform_sampling_matches_reference_golden(dev):
+    g = gu.load("replay_cases")
+    cap = 3000
+    h = dev.replay_create(cap, S, A, prioritized=False)
+    _fill(dev, h, cap)
+    for size in (cap, 1234, 1):
+        dev.check(dev.lib.b200rl_replay_set_cursor(h, 0, size % cap, size))
+        idx, _, _ = dev.replay_sample(h, 256, S, A, u=g[f"uni/{size}/u"])
+        assert np.array_equal(idx[0], g[f"uni/{size}/ind"])
+    dev.check(dev.lib.b200rl_replay_destroy(h))
+
+
+def test_lap_sampling_one_million_rows(dev):
+    """The size BASELINE.json quotes: 1M priorities, indices bit-exact vs the reference."""
+    g = gu.load("replay_cases")
+    big = (np.maximum(np.abs(np.random.default_rng(11).standard_normal(1_000_000) * 3), 1.0) ** 0.4).astype(np.float32)
+    h = dev.replay_create(1_000_000, 2, 1)
+    dev.replay_write_priority(h, big)
+    dev.check(dev.lib.b200rl_replay_set_cursor(h, 0, 0, 1_000_000))
+    idx, _, _ = dev.replay_sample(h, 256, 2, 1, u=g["big/u"])
+    assert np.array_equal(idx[0], g["big/ind"])
+    dev.check(dev.lib.b200rl_replay_destroy(h))
+
+
+def test_append_ring_wrap_scatter_and_running_max(dev):
+    g = gu.load("replay_cases")
+    cap = 3000
+    h = dev.replay_create(cap, S, A)
+    ref = oreplay.OracleLAP(cap, "Hopper-v4")
+    n = 3500
+    act_norm = (g["wrap/act"] / ref.action_scale - ref.action_bias).astype(np.float32)
+    packed = dev.pack_rows(h, g["wrap/obs"], act_norm, g["wrap/rew"], g["wrap/next_obs"], g["wrap/notdone"])
+    # one row at a time up to the mid-stream priority update, then in bulk across the wrap point
+    for i in range(1701):
+        dev.replay_append(h, packed[i:i + 1])
+        ref.append([g["wrap/obs"][i], g["wrap/act"][i], float(g["wrap/rew"][i]), g["wrap/next_obs"][i], float(g["wrap/notdone"][i])])
+    idx, _, _ = dev.replay_sample(h, 64, S, A, u=g["wrap/mid_u"])
+    assert np.array_equal(idx[0], g["wrap/mid_ind"])
+    ref.sample(64, u=torch.tensor(g["wrap/mid_u"]))
+    pr = dev.to_dev(g["wrap/mid_prio"])
+    dev.check(dev.lib.b200rl_replay_update_priority(h, pr, 64, None))
+    ref.update_priority(torch.tensor(g["wrap/mid_prio"]))
+    dev.replay_append(h, packed[1701:n])
+    for i in range(1701, n):
+        ref.append([g["wrap/obs"][i], g["wrap/act"][i], float(g["wrap/rew"][i]), g["wrap/next_obs"][i], float(g["wrap/notdone"][i])])
+    ptr, size, maxp = dev.replay_state(h)
+    assert [ptr, size, ptr] == list(g["wrap/ptr_size_len"])
+    assert maxp == float(g["wrap/max_priority"])
+    assert np.array_equal(dev.replay_priority(h, cap), g["wrap/priority"])
+    stride = dev.lib.b200rl_replay_row_stride(h)
+    rows = np.empty((cap, stride), np.float32)
+    dev.check(dev.lib.b200rl_replay_read_rows(h, 0, 0, cap, rows.ctypes.data, None))
+    assert np.array_equal(rows[:, :S], ref.state.astype(np.float32))
+    assert np.array_equal(rows[:, S:S + A], ref.action.astype(np.float32))
+    assert np.array_equal(rows[:, S + A + 2:2 * S + A + 2], ref.next_state.astype(np.float32))
+    dev.check(dev.lib.b200rl_replay_destroy(h))
+
+
+def test_duplicate_scatter_last_wins_and_reset(dev):
+    g = gu.load("replay_cases")
+    cap = 3000
+    h = dev.replay_create(cap, S, A)
+    _fill(dev, h, cap)
+    dev.replay_write_priority(h, np.ones(cap, np.float32), max_priority=1.0)
+    # force the "last sampled indices" through a sample whose draws hit exactly those rows:
+    # with all-ones priorities, u = (i + 0.5) / cap selects row i
+    want = g["dup/ind"]
+    u = ((want + 0.5) / cap).astype(np.float32)
+    idx, _, _ = dev.replay_sample(h, len(want), S, A, u=u)
+    assert np.array_equal(idx[0], want)
+    pr = dev.to_dev(g["dup/prio"])
+    dev.check(dev.lib.b200rl_replay_update_priority(h, pr, len(want), None))
+    assert np.array_equal(dev.replay_priority(h, cap), g["dup/priority_after"])
+    assert dev.replay_state(h)[2] == float(g["dup/max_priority"])
+    pri = dev.replay_priority(h, cap)
+    pri[100] = 1.0
+    dev.replay_write_priority(h, pri)
+    dev.check(dev.lib.b200rl_replay_reset_max_priority(h, None))
+    assert dev.replay_state(h)[2] == float(g["dup/max_after_reset"])
+    dev.check(dev.lib.b200rl_replay_destroy(h))
+
+
+def test_stacked_seeds_share_rows_and_device_rng(dev):
+    """groups > 1 with shared transitions: each seed samples with its own priorities; the
+    on-device Philox draws stay in range and differ between seeds."""
+    cap, G = 5000, 3
+    h = dev.replay_create(cap, S, A, groups=G, share_rows=True)
+    rows = None
+    for gidx in range(G):
+        rows = _fill(dev, h, cap, group=gidx)
+    rng = np.random.default_rng(5)
+    pris = [rng.uniform(1, 8, cap).astype(np.float32) for _ in range(G)]
+    for gidx in range(G):
+        dev.replay_write_priority(h, pris[gidx], group=gidx)
+    u = rng.random((G, 128), dtype=np.float32)
+    idx, batch, _ = dev.replay_sample(h, 128, S, A, u=u, groups=G)
+    for gidx in range(G):
+        assert np.array_equal(idx[gidx], oreplay.sample_indices_numpy(pris[gidx], u[gidx]))
+        assert np.array_equal(batch["state"][gidx], rows["state"][idx[gidx]])
+    idx2, _, _ = dev.replay_sample(h, 128, S, A, u=None, groups=G)
+    assert idx2.min() >= 0 and idx2.max() < cap
+    assert not np.array_equal(idx2[0], idx2[1])
+    dev.check(dev.lib.b200rl_replay_destroy(h))
