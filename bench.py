@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- gradient updates/sec of the off-policy update hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+One "step" = one update = ``replay.sample(256)`` + ``agent.train_ops(...)`` incl. priority write-back
+and the amortised delayed actor step / target sync.  Prints ONE JSON line (rank 0).
+
+* value   : updates/s with everything resident on the device (burst API ``train_ops_n``), timed with
+            CUDA events, max over ranks; whole-job aggregate over N GPUs (independent agents per GPU:
+            the per-agent update does not shard -- "replicas", weak scaling).
+* e2e     : the same metric through the reference-facing Python API with HOST data in the loop: every
+            step appends one transition from pinned host memory (H2D), samples, runs ``train_ops`` and
+            reads the info floats back (D2H + sync), as ``rl/runner/run.py:160-171`` drives it.
+* roofline: the dominant kernel (grouped FFMA GEMM) and, separately, the HBM-bound LAP tile-sum kernel.
+* cpu_baseline / --impl reference: the oracle port of the reference's CPU update loop (the reference is
+            pure Python and cannot travel to the GPU box), all host threads, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (algo, env, prioritized, seeds stacked per GPU, buffer rows)
+    "td7_halfcheetah_1M": ("TD7", "HalfCheetah-v4", True, 1, 1_000_000),
+    "td7_humanoid_1M": ("TD7", "Humanoid-v4", True, 1, 1_000_000),
+    "td7_ant_1M": ("TD7", "Ant-v4", True, 1, 1_000_000),
+    "td3_hopper_1M": ("TD3", "Hopper-v4", False, 1, 1_000_000),
+    "sac_walker2d_1M": ("SAC", "Walker2d-v4", False, 1, 1_000_000),
+    "td7_ant_pop256": ("TD7", "Ant-v4", True, 256, 1_000_000),
+    "td7_humanoid_pop256": ("TD7", "Humanoid-v4", True, 256, 200_000),
+}
+DEFAULT_WORKLOAD = "td7_halfcheetah_1M"  # BASELINE.json configs[1]
+ENV_DIMS = {"Hopper-v4": (11, 3), "HalfCheetah-v4": (17, 6), "Walker2d-v4": (17, 6), "Ant-v4": (27, 8), "Humanoid-v4": (376, 17)}
+BATCH = 256
+
+
+def algorithmic_gflop(algo: str, S: int, A: int, B: int = BATCH, H: int = 256, Z: int = 256) -> float:
+    """Necessary FLOPs of one update (SURVEY.md section 8d formulas; 2 FLOPs per MAC)."""
+    if algo == "TD7":
+        Es, Esa = S * H + 2 * H * H, (Z + A) * H + 2 * H * H
+        PI = S * H + (Z + H) * H + H * H + H * A
+        Q = (S + A) * H + (2 * Z + H) * H + H * H + H
+        enc = 3 * Es + 2 * Esa + 2 * H * H + (Z * H + 2 * H * H)
+        cri = 2 * Es + PI + 2 * Esa + 4 * Q + 2 * Q + 2 * (H + 2 * H * H)
+        act = Es + PI + Esa + 2 * Q + 2 * (H + H * H + (H + Z) * H + A * H) + (H * Z + H * H + A * H) + PI + (H * A + 2 * H * H)
+        macs = enc + cri + 0.5 * act
+    else:
+        Aout = 2 * A if algo == "SAC" else A
+        PI = S * H + H * H + H * Aout
+        Q = (S + A) * H + H * H + H
+        cri = PI + 4 * Q + 2 * Q + 2 * (H + H * H)
+        act = PI + 2 * Q + 2 * (H + H * H + A * H) + PI + (H * Aout + H * H)
+        macs = cri + (act if algo == "SAC" else 0.5 * act)
+    return 2.0 * macs * B / 1e9
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_updates_per_s(workload: str, budget_s: float, steps: int | None = None, warmup: int = 5):
+    """The reference's CPU update loop (oracle port: same torch ops in the same order, pinned bit-exact to
+    the reference by tests/test_oracle_golden.py) on this host, all threads."""
+    import torch
+
+    from oracle import agents as oagents
+    from oracle import replay as oreplay
+
+    algo, env, prio, _, rows = WORKLOADS[workload]
+    torch.manual_seed(0)
+    agent = {"TD7": oagents.OracleTD7, "TD3": oagents.OracleTD3, "SAC": oagents.OracleSAC}[algo](env, use_lap=prio)
+    buf = (oreplay.OracleLAP if prio else oreplay.OracleUniform)(rows, env)
+    buf.fill_synthetic(rows, seed=0)
+    for _ in range(warmup):
+        agent.train_ops(buf.sample(BATCH), replay_buffer=buf)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        agent.train_ops(buf.sample(BATCH), replay_buffer=buf)
+        n += 1
+        el = time.perf_counter() - t0
+        if (steps is not None and n >= steps) or (steps is None and el >= budget_s):
+            break
+        if el > 180:
+            break
+    return n / el, n, el, torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    ups, n, el, threads = cpu_updates_per_s(args.workload, budget_s=20.0, steps=args.steps if args.steps_given else None, warmup=max(args.warmup, 3))
+    algo, env, prio, seeds, rows = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": "gradient updates/sec (batch 256) per agent", "value": ups, "unit": "updates/s", "n_gpus": args.gpus,
+        "steps": n, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 / ups, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "algo": algo, "env": env, "batch": BATCH, "buffer_rows": rows, "replay": "LAP" if prio else "uniform"},
+        "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": threads, "kind": "port",
+                         "sample": f"{n} updates of the oracle port (torch {torch.__version__} CPU, {threads} threads, os.cpu_count={os.cpu_count()}) in {el:.1f}s"},
+        "e2e": {"value": ups, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            d = json.load(fh)
+        return d["hbm_gbs"], d["bf16_tflops"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, 1590.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+def gemm_roofline(lib, torch, S, A, groups=1):
+    """Time the largest grouped launch of the TD7 critic chain (csrc/agent_td7.cuh table C[7]: five
+    independent layers, K up to 768) standalone with CUDA events."""
+    from sac_td3_td7_b200 import _lib
+
+    B, H, Z = BATCH, 256, 256
+    dev = torch.device("cuda")
+    mk = lambda *s: torch.randn(*s, device=dev) * 0.05  # noqa: E731
+    probs, flops, keep = [], 0.0, []
+
+    def add(xs, n_out):
+        nonlocal flops
+        K = sum(x.shape[1] for x in xs)
+        ld = (K + 3) // 4 * 4
+        W, b, y = mk(n_out, ld), mk(n_out), torch.empty(B, n_out, device=dev)
+        keep.extend([W, b, y, *xs])
+        p = _lib.GemmProblem()
+        p.I, p.J, p.C, p.c_ld, p.act, p.bias = B, n_out, y.data_ptr(), n_out, 2, b.data_ptr()
+        off = 0
+        for x in xs:
+            s = p.seg[p.nseg]
+            s.A, s.a_ld, s.B, s.b_ld, s.len = x.data_ptr(), x.shape[1], W.data_ptr() + 4 * off, ld, x.shape[1]
+            p.nseg += 1
+            off += x.shape[1]
+        probs.append(p)
+        flops += 2.0 * B * n_out * K
+
+    zs, a, s2, qn, zsa = mk(B, Z), mk(B, A), mk(B, S), mk(B, H), mk(B, Z)
+    add([zs, a], H)            # fixed_encoder_target.zsa1
+    add([s2, a], H)            # target_q1.q01
+    add([s2, a], H)            # target_q2.q01
+    add([qn, zsa, zs], H)      # q1.q1
+    add([qn, zsa, zs], H)      # q2.q1
+    arr = (_lib.GemmProblem * len(probs))(*probs)
+    ms = C.c_float()
+    _lib.check(lib.b200rl_op_gemm_timed(0, arr, len(probs), groups, 20, 200, C.byref(ms), torch.cuda.current_stream().cuda_stream))
+    return flops, ms.value
+
+
+def run_gpu_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from sac_td3_td7_b200 import _lib, build
+    from sac_td3_td7_b200.rl.agent import SAC, TD3, TD7
+    from sac_td3_td7_b200.rl.replay_memory import LAPReplayMemory, SimpleReplayMemory
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the update path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+    lib = _lib.lib()
+
+    algo, env, prio, seeds, rows = WORKLOADS[args.workload]
+    S, A = ENV_DIMS[env]
+    K, W = args.steps, max(args.warmup, 3)
+    torch.manual_seed(1000 + rank)
+    cls = {"TD7": TD7, "TD3": TD3, "SAC": SAC}[algo]
+    agent = cls(env, use_lap=prio, n_seeds=seeds) if algo != "SAC" else cls(env, n_seeds=seeds)
+    buf = (LAPReplayMemory if prio else SimpleReplayMemory)(rows, env, n_seeds=seeds, share_rows=seeds > 1)
+    buf.fill_synthetic(rows, seed=rank)
+    stream = torch.cuda.current_stream()
+
+    # ---- device-resident throughput: K updates through the burst API ----
+    agent.train_ops_n(W, buf)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    infos = agent.train_ops_n(K, buf)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    last = {k: (None if v is None else float(v)) for k, v in infos[-1].items()}
+    clk = clocks.stop() if clocks else None
+    t = torch.tensor([ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    ms_max = float(t.item())
+    value = world * seeds * K / (ms_max / 1e3)
+
+    # ---- end to end through the drop-in API with host data in the loop ----
+    e2e_steps = min(K, 2000)
+    g = np.random.default_rng(5)
+    pinned = torch.empty((64, buf.row_stride), dtype=torch.float32).pin_memory()
+    pinned.copy_(torch.from_numpy(buf.pack(g.standard_normal((64, S), dtype=np.float32), g.random((64, A), dtype=np.float32) * 2 - 1,
+                                           g.standard_normal((64, 1), dtype=np.float32), g.standard_normal((64, S), dtype=np.float32),
+                                           np.ones((64, 1), np.float32))))
+    pinned_np = pinned.numpy()
+
+    def e2e_step(i):
+        for s in range(seeds if not buf.share_rows else 1):
+            buf.append_rows(pinned_np[i % 64:i % 64 + 1], s)            # H2D of one transition from pinned memory
+        batch = buf.sample(BATCH)
+        info = agent.train_ops(batch, replay_buffer=buf)
+        return float(info["train/q_fn"])                                   # D2H of the info row + sync
+
+    e2e = None
+    if seeds == 1:
+        for i in range(W):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        t = torch.tensor([el], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * e2e_steps / float(t.item()), "unit": "updates/s", "h2d_bytes_per_step": buf.row_stride * 4,
+               "d2h_bytes_per_step": 4 * len(agent.INFO_KEYS), "steps": e2e_steps,
+               "note": "per step: append 1 transition from pinned host memory, sample(256), train_ops, read info floats (sync)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- rooflines (rank 0, standalone event-timed launches) ----
+    hbm_peak, bf16_burst, bf16_sus, peak_src = measured_peaks()
+    g_flops, g_ms = gemm_roofline(lib, torch, S, A)
+    ach_tf = g_flops / (g_ms * 1e-3) / 1e12
+    roofline = {"kernel": "gemm_kernel<fwd> (grouped FFMA GEMM, 5 independent layers of the TD7 critic chain, 320 CTAs)", "bound": "tensor",
+                "achieved": ach_tf, "peak": bf16_burst, "unit": "TFLOP/s", "frac": ach_tf / bf16_burst, "traffic": None,
+                "peak_source": peak_src + ", dense bf16 cuBLAS burst",
+                "note": "fp32 FFMA by design (1e-5 fp32 parity rules out single-pass TF32/BF16); the non-tensor fp32 peak of a B200 is ~74.5 TFLOP/s",
+                "fp32_ffma_peak_tflops": 74.5, "frac_of_fp32_ffma_peak": ach_tf / 74.5, "launch_ms": g_ms, "flops_per_launch": g_flops}
+    roof2 = None
+    if prio:
+        ms2 = (C.c_float * 2)()
+        _lib.check(lib.b200rl_replay_time_sample(buf._h, BATCH, 10, 200, ms2, stream.cuda_stream))
+        bytes_scan = 4.0 * rows * seeds
+        row_bytes = 4.0 * (2 * S + A + 2)
+        bytes_gather = seeds * (BATCH * row_bytes * 2 + BATCH * (4 + 8) + (rows / 256) * 8)
+        roof2 = {"kernel": "lap_tile_sums_kernel (fp64 tile sums over all priorities)", "bound": "hbm", "achieved": bytes_scan / (ms2[0] * 1e-3) / 1e9,
+                 "peak": hbm_peak, "unit": "GB/s", "frac": bytes_scan / (ms2[0] * 1e-3) / 1e9 / hbm_peak, "traffic": None, "launch_ms": ms2[0],
+                 "bytes_per_launch": bytes_scan, "peak_source": peak_src,
+                 "note": "4 MB per seed: L2-resident for one agent (latency-bound launch); HBM-bound only when hundreds of seeds are stacked",
+                 "search_gather_kernel": {"launch_ms": ms2[1], "bytes_per_launch": bytes_gather, "achieved_gbs": bytes_gather / (ms2[1] * 1e-3) / 1e9}}
+
+    # ---- CPU baseline (oracle port) on this host, bounded ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        ups, n, el, threads = cpu_updates_per_s(args.workload if seeds == 1 else "td7_ant_1M", budget_s=15.0)
+        cpu = {"value": ups, "unit": "updates/s", "cores": threads, "kind": "port",
+               "sample": f"{n} updates of the oracle port of the reference CPU loop ({threads} torch threads, os.cpu_count={os.cpu_count()}) in {el:.1f}s, same workload"}
+
+    lp0, lp1 = lib.b200rl_agent_launches_per_update(agent._h, 0), lib.b200rl_agent_launches_per_update(agent._h, 1)
+    per_update = (lp0 + lp1) / 2.0 if algo != "SAC" else float(lp1)
+    gflop = algorithmic_gflop(algo, S, A)
+    line = {
+        "metric": "gradient updates/sec (batch 256) per agent" if seeds == 1 else "agent-updates/sec (batch 256)",
+        "value": value, "unit": "updates/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "algo": algo, "env": env, "obs_dim": S, "act_dim": A, "batch": BATCH, "buffer_rows": rows,
+                   "replay": "LAP" if prio else "uniform", "seeds_per_gpu": seeds, "parallelism": f"replicas x{world} (independent agents, no data-path collective)",
+                   "l2": "replay rows exceed L2 (1M rows); weights, Adam moments and the 4 MB priority array are L2-resident by design -- they are the loop state"},
+        "e2e": e2e, "gpu_launches": int(K * (per_update + (2 if prio else 1))), "launches_per_update": {"critic_only": lp0, "with_actor": lp1},
+        "clocks": clk, "roofline": roofline, "roofline_replay": roof2, "cpu_baseline": cpu,
+        "algorithmic_gflop_per_update": gflop, "update_tflops_per_gpu": gflop * value / 1e3 / world,
+        "last_info": last,
+    }
+    if cpu:
+        line["speedup_vs_cpu_port"] = {"device_resident": value / cpu["value"], "e2e": (e2e["value"] / cpu["value"]) if e2e else None}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.steps_given = args.steps is not None
+    if args.steps is None:
+        args.steps = 2000
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -183,6 +183,12 @@ typedef struct {
 /* mode: 0 forward (Y = X W^T + b, activation), 1 dgrad (dX = dZ W, times act'), 2 wgrad (dW = dZ^T X,
  * optional fused Adam).  act: 0 none, 1 ReLU, 2 ELU, 3 tanh, 4 tanh + clipped noise + clamp. */
 int b200rl_op_gemm(int mode, const b200rl_gemm_problem* problems_host, int nproblems, int groups, void* stream);
+/* same launch repeated `iters` times after `warmup` launches, timed with CUDA events on `stream`;
+ * returns the mean device time of one launch in milliseconds (bench.py roofline) */
+int b200rl_op_gemm_timed(int mode, const b200rl_gemm_problem* problems_host, int nproblems, int groups, int warmup, int iters, float* ms_per_launch,
+                         void* stream);
+/* mean device time (ms) of the two sampler kernels for the current buffer contents: [0] tile sums, [1] search+gather */
+int b200rl_replay_time_sample(b200rl_replay* h, int batch, int warmup, int iters, float* ms_out2, void* stream);
 /* rl/nn/sale.py:11-13 AvgL1Norm forward (y = x / max(mean|x|, 1e-8)) and its backward */
 int b200rl_op_avgl1norm(int backward, const float* x_dev, const float* dy_dev, float* y_dev, int rows, int n, void* stream);
 /* torch.optim.Adam single-tensor step `step` (1-based) on n floats */

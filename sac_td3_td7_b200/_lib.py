@@ -114,6 +114,8 @@ SIGNATURES = {
     "b200rl_agent_launches_per_update": (C.c_int, [c_vp, C.c_int]),
     # ops
     "b200rl_op_gemm": (C.c_int, [C.c_int, C.POINTER(GemmProblem), C.c_int, C.c_int, c_vp]),
+    "b200rl_op_gemm_timed": (C.c_int, [C.c_int, C.POINTER(GemmProblem), C.c_int, C.c_int, C.c_int, C.c_int, c_f32p, c_vp]),
+    "b200rl_replay_time_sample": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, c_f32p, c_vp]),
     "b200rl_op_avgl1norm": (C.c_int, [C.c_int, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp]),
     "b200rl_op_adam": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, c_vp]),
     "b200rl_op_polyak": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_double, c_vp]),

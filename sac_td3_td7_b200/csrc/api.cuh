@@ -532,6 +532,84 @@ int b200rl_op_gemm(int mode, const b200rl_gemm_problem* problems_host, int nprob
   B200_CHECK_CUDA(cudaStreamSynchronize(as_stream(stream)));
   return kOk;
 }
+int b200rl_op_gemm_timed(int mode, const b200rl_gemm_problem* problems_host, int nproblems, int groups, int warmup, int iters, float* ms_per_launch, void* stream) {
+  B200_REQUIRE(problems_host && nproblems > 0 && groups > 0 && iters > 0 && ms_per_launch, "bad arguments");
+  B200_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0..2");
+  B200_TRY(ensure_device());
+  std::vector<GemmProblem> v(nproblems);
+  memcpy(v.data(), problems_host, (size_t)nproblems * sizeof(GemmProblem));
+  DeviceArena tmp;
+  GemmTable t;
+  B200_TRY(gemm_table_upload(&t, mode, v, &tmp));
+  cudaStream_t s = as_stream(stream);
+  for (int i = 0; i < warmup; ++i) B200_TRY(gemm_table_launch(t, groups, s));
+#ifndef B200_EMU
+  cudaEvent_t e0, e1;
+  B200_CHECK_CUDA(cudaEventCreate(&e0));
+  B200_CHECK_CUDA(cudaEventCreate(&e1));
+  B200_CHECK_CUDA(cudaEventRecord(e0, s));
+  for (int i = 0; i < iters; ++i) B200_TRY(gemm_table_launch(t, groups, s));
+  B200_CHECK_CUDA(cudaEventRecord(e1, s));
+  B200_CHECK_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  B200_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_launch = ms / (float)iters;
+#else
+  for (int i = 0; i < iters; ++i) B200_TRY(gemm_table_launch(t, groups, s));
+  *ms_per_launch = 0.f;
+#endif
+  return kOk;
+}
+int b200rl_replay_time_sample(b200rl_replay* h, int batch, int warmup, int iters, float* ms_out2, void* stream) {
+  B200_REQUIRE(h && ms_out2 && iters > 0, "bad arguments");
+  Replay& r = h->r;
+  long long n;
+  B200_TRY(r.common_size(&n));
+  B200_REQUIRE(n > 0, "buffer is empty");
+  DeviceArena tmp;
+  float *st, *ac, *rw, *ns, *dn;
+  const int G = r.groups;
+  B200_TRY(tmp.alloc(&st, (size_t)G * batch * r.S)); B200_TRY(tmp.alloc(&ns, (size_t)G * batch * r.S));
+  B200_TRY(tmp.alloc(&ac, (size_t)G * batch * r.A)); B200_TRY(tmp.alloc(&rw, (size_t)G * batch)); B200_TRY(tmp.alloc(&dn, (size_t)G * batch));
+  Replay::Outputs o;
+  o.state = st; o.ld_state = r.S; o.state_gs = (long long)batch * r.S;
+  o.next_state = ns; o.ld_next = r.S; o.next_gs = (long long)batch * r.S;
+  o.action = ac; o.ld_action = r.A; o.action_gs = (long long)batch * r.A;
+  o.reward = rw; o.reward_gs = batch; o.done = dn; o.done_gs = batch;
+  cudaStream_t s = as_stream(stream);
+  ms_out2[0] = ms_out2[1] = 0.f;
+#ifndef B200_EMU
+  const int ntiles = ceil_div((int)n, kPrioTile);
+  cudaEvent_t e0, e1;
+  B200_CHECK_CUDA(cudaEventCreate(&e0));
+  B200_CHECK_CUDA(cudaEventCreate(&e1));
+  for (int i = 0; i < warmup; ++i) B200_TRY(r.sample(batch, nullptr, o, s));
+  if (r.prioritized) {
+    dim3 grid((unsigned)ceil_div(ntiles, kPrioTilesPerCta), (unsigned)G), block(256);
+    B200_CHECK_CUDA(cudaEventRecord(e0, s));
+    for (int i = 0; i < iters; ++i) B200_LAUNCH(lap_tile_sums_kernel, grid, block, 0, s, r.d_priority, r.cap_pad, (int)n, r.d_tile_sums, ntiles, (long long)r.max_tiles);
+    B200_CHECK_CUDA(cudaEventRecord(e1, s));
+    B200_CHECK_CUDA(cudaEventSynchronize(e1));
+    B200_CHECK_CUDA(cudaEventElapsedTime(&ms_out2[0], e0, e1));
+    ms_out2[0] /= (float)iters;
+  }
+  B200_CHECK_CUDA(cudaEventRecord(e0, s));
+  for (int i = 0; i < iters; ++i) B200_TRY(r.sample(batch, nullptr, o, s));
+  B200_CHECK_CUDA(cudaEventRecord(e1, s));
+  B200_CHECK_CUDA(cudaEventSynchronize(e1));
+  float both = 0.f;
+  B200_CHECK_CUDA(cudaEventElapsedTime(&both, e0, e1));
+  ms_out2[1] = both / (float)iters - ms_out2[0];
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+#else
+  (void)warmup;
+  for (int i = 0; i < iters; ++i) B200_TRY(r.sample(batch, nullptr, o, s));
+#endif
+  return kOk;
+}
 int b200rl_op_avgl1norm(int backward, const float* x_dev, const float* dy_dev, float* y_dev, int rows, int n, void* stream) {
   B200_REQUIRE(x_dev && y_dev && rows > 0 && n > 0 && (!backward || dy_dev), "bad arguments");
   B200_TRY(ensure_device());

@@ -1,0 +1,151 @@
+"""The Python drop-in layer (sac_td3_td7_b200.rl.*) on a real GPU, driven the way the reference's
+runner drives it (rl/runner/run.py:87-96), against the oracle."""
+import copy
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(name):
+    from sac_td3_td7_b200.rl.agent import SAC, TD3, TD7
+    from sac_td3_td7_b200.rl.replay_memory import LAPReplayMemory, SimpleReplayMemory
+
+    algo, env_id, prioritized, kwargs, steps = gu.CASES[name]
+    torch.manual_seed(gu.SEED)
+    cls = {"TD7": TD7, "TD3": TD3, "SAC": SAC}[algo]
+    agent = cls(env_id, **kwargs)
+    buf = (LAPReplayMemory if prioritized else SimpleReplayMemory)(gu.BUFFER_ROWS, env_id)
+    buf.fill_synthetic(gu.BUFFER_ROWS - 96, seed=gu.SEED)
+    return agent, buf, algo, steps
+
+
+@pytest.mark.parametrize("name", ["td7_halfcheetah_lap", "td3_hopper_uniform", "sac_walker2d"])
+def test_runner_style_loop_matches_reference_golden(name):
+    """Same seed => same initial weights as the reference; the reference's recorded draws; the
+    reference's recorded infos / indices (free-running, so fp32 drift tolerance on the losses)."""
+    g = gu.load(name)
+    agent, buf, algo, steps = _mk(name)
+    for t in range(steps):
+        batch = buf.sample(gu.BATCH, u=torch.tensor(g[f"s{t}/u"]))
+        assert np.array_equal(buf.ind, g[f"s{t}/ind"]), f"step {t}"
+        assert np.array_equal(batch["action"].cpu().numpy(), g[f"s{t}/batch_action"])
+        assert batch["state"].shape == (gu.BATCH, agent.state_dim) and batch["reward"].shape == (gu.BATCH, 1)
+        info = agent.train_ops(batch, replay_buffer=buf, noise=gu.step_noise(g, t, algo))
+        for k, v in info.items():
+            ref = float(g[f"s{t}/info/{k}"])
+            if v is None:
+                assert np.isnan(ref)
+            else:
+                assert abs(float(v) - ref) <= 2e-3 * max(abs(ref), 1e-2), (t, k, float(v), ref)
+                assert f"{v:.4f}" == f"{float(v):.4f}"
+        if buf.prioritized:
+            assert abs(buf.max_priority - float(g[f"s{t}/max_priority"])) <= 1e-4 * float(g[f"s{t}/max_priority"])
+    assert len(buf) == buf.ptr and buf.size == gu.BUFFER_ROWS - 96
+    act = agent.sample(g["act/obs"], True)
+    assert np.abs(act - g["act/action"]).max() < 5e-3
+    # run.py:47-51 mean over infos with None entries
+    vals = [i for i in [info.get("train/q_fn")] if i is not None]
+    assert sum(vals) / len(vals) == pytest.approx(float(vals[0]))
+
+
+def test_burst_api_and_device_rng():
+    agent, buf, algo, _ = _mk("td7_halfcheetah_lap")
+    infos = agent.train_ops_n(12, buf)
+    assert len(infos) == 12 and agent.n_runs == 12
+    assert [i["train/policy"] is not None for i in infos] == [(k + 1) % 2 == 0 for k in range(12)]
+    q = [float(i["train/q_fn"]) for i in infos]
+    assert all(np.isfinite(q)) and all(0.1 < x < 10 for x in q)
+    assert buf.max_priority >= 1.0
+    pri = buf.priority[: buf.size]
+    assert float(pri.min()) >= 1.0 and float(pri.max()) > 1.0  # priorities were written back
+
+
+def test_state_dict_modules_deepcopy_load_save():
+    from sac_td3_td7_b200.rl.agent import TD7, Agent
+
+    agent, buf, algo, _ = _mk("td7_halfcheetah_lap")
+    w0 = agent.policy.l1.weight.detach().clone()
+    agent.train_ops_n(4, buf)
+    w1 = agent.policy.l1.weight.detach().clone()
+    assert not torch.equal(w0, w1)                       # host modules follow the device weights
+    assert agent.target_policy is agent.policy           # aliased, SURVEY.md B.1
+    twin = copy.deepcopy(agent)                           # run_w_checkpoint.py:72
+    assert torch.equal(twin.policy.l1.weight, w1) and twin.n_runs == agent.n_runs
+    agent.train_ops_n(2, buf)
+    assert not torch.equal(agent.q1.q2.weight, twin.q1.q2.weight)
+    twin.load_state_dict(agent)                           # run_w_checkpoint.py:140
+    assert torch.equal(agent.q1.q2.weight, twin.q1.q2.weight)
+    assert torch.equal(agent.fixed_encoder_target.zs1.weight, twin.fixed_encoder_target.zs1.weight)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "ckpt.pkl")
+        agent.to(torch.device("cpu")).to(torch.device("cuda"))
+        agent.save(path)                                  # abc.py:38-47
+        back = Agent.load(path)
+        assert isinstance(back, TD7) and back.n_runs == agent.n_runs
+        assert torch.equal(back.encoder.zsa3.weight, agent.encoder.zsa3.weight)
+        obs = np.linspace(-1, 1, agent.state_dim).astype(np.float32)
+        assert np.allclose(back.sample(obs, True), agent.sample(obs, True), atol=1e-6)
+        # the restored agent keeps training (optimizer moments and counters came along)
+        i1 = back.train_ops_n(2, buf)
+        assert np.isfinite(float(i1[-1]["train/q_fn"]))
+
+
+def test_nn_modules_forward_match_oracle():
+    from oracle import nets as onets
+    from sac_td3_td7_b200.rl import nn as bnn
+
+    torch.manual_seed(3)
+    S, A, B = 17, 6, 64
+    enc, pol, cri = bnn.SALEEncoder(S, A).cuda(), bnn.SALEActor(S, A).cuda(), bnn.SALECritic(S, A).cuda()
+    mlp_pi, mlp_q = bnn.MLPActor(S, 2 * A).cuda(), bnn.MLPCritic(S, A).cuda()
+    s, a = torch.randn(B, S), torch.rand(B, A) * 2 - 1
+    cpu = lambda m: {k: v.detach().cpu() for k, v in m.state_dict().items()}  # noqa: E731
+    zs = enc.encode_state(s.cuda())
+    zs_ref = onets.encode_state(cpu(enc), s)
+    assert torch.allclose(zs.cpu(), zs_ref, atol=2e-5, rtol=1e-5)
+    zsa = enc.encode_state_action(zs, a.cuda())
+    assert torch.allclose(zsa.cpu(), onets.encode_state_action(cpu(enc), zs_ref, a), atol=2e-5, rtol=1e-5)
+    assert torch.allclose(pol.inference_mean(s.cuda(), zs).cpu(), onets.sale_actor(cpu(pol), s, zs_ref), atol=2e-5)
+    q = cri.estimate_q_value(s.cuda(), a.cuda(), zsa, zs)
+    assert torch.allclose(q.cpu(), onets.sale_critic(cpu(cri), s, a, zsa.cpu(), zs_ref), atol=2e-5, rtol=1e-5)
+    mean, logvar = mlp_pi.inference_mean_logvar(s.cuda())
+    ref = onets.mlp(cpu(mlp_pi), s)
+    assert torch.allclose(torch.cat([mean, logvar], -1).cpu(), ref, atol=2e-5, rtol=1e-5)
+    assert torch.allclose(mlp_q.estimate_q_value(s.cuda(), a.cuda()).cpu(), onets.mlp_critic(cpu(mlp_q), s, a), atol=2e-5, rtol=1e-5)
+    x = torch.randn(B, 256)
+    assert torch.allclose(bnn.AvgL1Norm(x.cuda()).cpu(), onets.avg_l1_norm(x), atol=1e-6, rtol=1e-5)
+
+
+def test_append_from_rollout_and_uniform_buffer():
+    from oracle import replay as oreplay
+    from sac_td3_td7_b200.rl.replay_memory import LAPReplayMemory
+
+    env = "Humanoid-v4"  # action scale 0.4: exercises the a/scale - bias normalisation (lap.py:35)
+    buf, ref = LAPReplayMemory(500, env), oreplay.OracleLAP(500, env)
+    g = np.random.default_rng(0)
+    for i in range(620):
+        tr = [g.standard_normal(376).astype(np.float32), g.uniform(-0.4, 0.4, 17).astype(np.float32), float(g.standard_normal()),
+              g.standard_normal(376).astype(np.float32), 1.0 - float(i % 40 == 0)]
+        buf.append(copy.deepcopy(tr))
+        ref.append(copy.deepcopy(tr))
+    assert (len(buf), buf.size) == (len(ref), ref.size)
+    u = torch.rand(256)
+    b, rb = buf.sample(256, u=u), ref.sample(256, u=u)
+    assert np.array_equal(buf.ind, ref.ind)
+    for k in rb:
+        assert torch.equal(b[k].cpu(), rb[k]), k
+
+
+def test_no_cpu_fallback_paths():
+    from sac_td3_td7_b200 import _lib
+    from sac_td3_td7_b200.rl import nn as bnn
+
+    with pytest.raises(_lib.B200RLError):
+        bnn.AvgL1Norm(torch.randn(4, 8))  # CPU tensor: refused, not silently computed on the host
