@@ -98,13 +98,17 @@ struct AgentBase {
     nopt = nopt_;
     info_cols = info_cols_;
     B200_CHECK_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    B200_TRY(fork.init(stream, 3, 64));
+    B200_TRY(fork.init(stream, 4, 64));
     B200_TRY(arena.alloc(&d_step, 1));
     B200_TRY(arena.alloc(&d_adam, (size_t)nopt));
     B200_TRY(arena.alloc(&d_hyper, (size_t)nopt));
     B200_TRY(arena.alloc(&d_flags, 4));
     B200_TRY(arena.alloc(&d_info, (size_t)G * kInfoRing * info_cols));
     B200_CHECK_CUDA(cudaMemcpy(d_hyper, hyper, nopt * sizeof(OptimHyper), cudaMemcpyHostToDevice));
+    StepState st0;
+    memset(&st0, 0, sizeof(st0));
+    for (int k = 0; k < 4; ++k) st0.b1pow[k] = st0.b2pow[k] = 1.0;
+    B200_CHECK_CUDA(cudaMemcpy(d_step, &st0, sizeof(st0), cudaMemcpyHostToDevice));
     return kOk;
   }
 

@@ -177,7 +177,7 @@ struct MlpAgent : AgentBase {
       a.priority = bound->d_priority; a.max_priority = bound->d_max_priority; a.idx = bound->d_idx; a.prio_gs = bound->cap_pad;
       a.idx_gs = bound->max_batch;
     }
-    B200_LAUNCH(critic_loss_kernel, dim3((unsigned)G), dim3((unsigned)round_up(B, 32)), (size_t)B * sizeof(long long), s, a);
+    B200_LAUNCH(critic_loss_kernel, dim3((unsigned)G), dim3((unsigned)round_up(B, 32)), sizeof(ScatterTable), s, a);
     B200_CHECK_LAUNCH();
     return kOk;
   }
@@ -219,13 +219,16 @@ struct MlpAgent : AgentBase {
   // variant bit0: actor step (SAC: always)
   int issue_step(int variant) override {
     const bool actor = sac || (variant & 1);
-    cudaStream_t M = stream, sN = fork.side[0];
+    cudaStream_t M = stream, sN = fork.side[0], sP = fork.side[3];
     unsigned mask = 0x2u | (actor ? 0x1u : 0u) | ((sac && auto_tmp) ? 0x4u : 0u);
-    B200_TRY(launch_prep(mask, M));
-    B200_TRY(launch_gauss(noise, 0, M));
-    if (sac) B200_TRY(launch_gauss(noise2, 1, M));
+    B200_TRY(fork.link(M, sP));  // counters / Adam scalars / noise: off the critical path
+    B200_TRY(launch_prep(mask, sP));
+    B200_TRY(launch_gauss(noise, 0, sP));
+    if (sac) B200_TRY(launch_gauss(noise2, 1, sP));
     const int v = actor ? 1 : 0;
-    GL(T[v][0], M); GL(T[v][1], M); GL(T[v][2], M);
+    GL(T[v][0], M); GL(T[v][1], M);
+    B200_TRY(fork.link(sP, M));
+    GL(T[v][2], M);
     if (sac) {
       B200_TRY(launch_sample_fwd(pout_n, noise, a_next, logp_n, M));
       B200_TRY(fork.link(M, sN));

@@ -256,7 +256,7 @@ struct TD7Agent : AgentBase {
       a.priority = bound->d_priority; a.max_priority = bound->d_max_priority; a.idx = bound->d_idx; a.prio_gs = bound->cap_pad;
     }
     a.idx_gs = bound ? (long long)bound->max_batch : 0;
-    B200_LAUNCH(critic_loss_kernel, dim3((unsigned)G), dim3((unsigned)round_up(B, 32)), (size_t)B * sizeof(long long), s, a);
+    B200_LAUNCH(critic_loss_kernel, dim3((unsigned)G), dim3((unsigned)round_up(B, 32)), sizeof(ScatterTable), s, a);
     B200_CHECK_LAUNCH();
     return kOk;
   }
@@ -270,13 +270,16 @@ struct TD7Agent : AgentBase {
   // variant: bit0 = actor step
   int issue_step(int variant) override {
     const bool actor = (variant & 1) != 0;
-    cudaStream_t M = stream, sE = fork.side[0], sA = fork.side[1], sN = fork.side[2];
-    B200_TRY(launch_prep(actor ? 0x7u : 0x6u, M));  // optimizers: 0 policy, 1 critics, 2 encoder
-    B200_TRY(launch_gauss(noise, 0, M));
+    cudaStream_t M = stream, sE = fork.side[0], sA = fork.side[1], sN = fork.side[2], sP = fork.side[3];
+    // counters / Adam scalars / smoothing noise: off the critical path, joined where first needed
+    B200_TRY(fork.link(M, sP));
+    B200_TRY(launch_prep(actor ? 0x7u : 0x6u, sP));  // optimizers: 0 policy, 1 critics, 2 encoder
+    B200_TRY(launch_gauss(noise, 0, sP));
     // ---- encoder branch
     B200_TRY(fork.link(M, sE));
     GL(E[0], sE); GL(E[1], sE); GL(E[2], sE); RL(En[0], sE);
     GL(E[3], sE); GL(E[4], sE); GL(E[5], sE);
+    B200_TRY(fork.link(sP, sE));  // info slot (loss) and Adam scalars (wgrad)
     B200_TRY(launch_enc_loss(sE));
     GL(E[6], sE); GL(E[7], sE); GL(E[8], sE); RL(En[1], sE); GL(E[9], sE); GL(E[10], sE); GL(E[11], sE);
     // ---- critic chain
@@ -289,7 +292,9 @@ struct TD7Agent : AgentBase {
       B200_TRY(fork.link(M, sA));
       GL(Aa[0], sA); GL(Aa[1], sA); GL(Aa[2], sA); GL(Aa[3], sA); GL(Aa[4], sA); GL(Aa[5], sA);
     }
-    GL(C[4], M); GL(C[5], M); GL(C[6], M); GL(C[7], M);
+    GL(C[4], M); GL(C[5], M);
+    B200_TRY(fork.link(sP, M));  // smoothing noise for the policy's last layer; counters for the loss / Adam
+    GL(C[6], M); GL(C[7], M);
     B200_TRY(fork.link(M, sN));
     RL(Cn[3], sN);
     GL(C[8], M); GL(C[9], M);

@@ -382,7 +382,14 @@ int b200rl_agent_set_counters(b200rl_agent* h, int64_t n_runs, const int64_t* ad
   StepState st;
   memset(&st, 0, sizeof(st));
   st.n_runs = (int)n_runs;
-  for (int k = 0; k < 3; ++k) st.adam_t[k] = (int)adam_steps[k];
+  std::vector<OptimHyper> hy(h->base->nopt);
+  B200_CHECK_CUDA(cudaMemcpy(hy.data(), h->base->d_hyper, hy.size() * sizeof(OptimHyper), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 4; ++k) st.b1pow[k] = st.b2pow[k] = 1.0;
+  for (int k = 0; k < 3 && k < h->base->nopt; ++k) {
+    st.adam_t[k] = (int)adam_steps[k];
+    st.b1pow[k] = pow(hy[k].beta1, (double)adam_steps[k]);
+    st.b2pow[k] = pow(hy[k].beta2, (double)adam_steps[k]);
+  }
   B200_CHECK_CUDA(cudaMemcpyAsync(h->base->d_step, &st, sizeof(st), cudaMemcpyHostToDevice, as_stream(stream)));
   B200_CHECK_CUDA(cudaStreamSynchronize(as_stream(stream)));
   h->base->n_calls = n_runs;
@@ -628,6 +635,8 @@ int b200rl_op_adam(float* p_dev, float* m_dev, float* v_dev, const float* g_dev,
   StepState* st; AdamScalars* sc; OptimHyper* hy;
   B200_TRY(tmp.alloc(&st, 1)); B200_TRY(tmp.alloc(&sc, 1)); B200_TRY(tmp.alloc(&hy, 1));
   StepState h0; memset(&h0, 0, sizeof(h0)); h0.adam_t[0] = step - 1;
+  for (int k = 0; k < 4; ++k) h0.b1pow[k] = h0.b2pow[k] = 1.0;
+  h0.b1pow[0] = pow(beta1, (double)(step - 1)); h0.b2pow[0] = pow(beta2, (double)(step - 1));
   OptimHyper hh{lr, beta1, beta2, eps};
   B200_CHECK_CUDA(cudaMemcpy(st, &h0, sizeof(h0), cudaMemcpyHostToDevice));
   B200_CHECK_CUDA(cudaMemcpy(hy, &hh, sizeof(hh), cudaMemcpyHostToDevice));

@@ -17,13 +17,16 @@
 // applies Adam in place (torch.optim.Adam single-tensor ordering), so gradients never
 // round-trip through HBM in the stacked-seed case.
 //
-// Tiling: CTA = 128 threads, 32x32 output tile, 32-deep reduction chunks, double-buffered
-// through registers.  The four warps split each chunk's reduction (8 r's each) and every
-// lane owns a 4x8 register tile (32 FFMA per 3 LDS.128); partial tiles are summed in a
-// fixed order through shared memory, so results are bit-reproducible run to run.
-// Shared tiles are stored reduction-major with an XOR swizzle at float4 granularity so
-// that both the transposing stores (r-contiguous global operands) and the float4 reads
-// are bank-conflict free.
+// Tiling: CTA = 256 threads, 32x32 output tile, 32-deep reduction chunks in a 3-stage
+// cp.async (LDGSTS) pipeline: every thread issues one 16-byte copy per operand per chunk
+// straight from global/L2 into shared memory (no register staging, no transposition), two
+// chunks ahead of the math.  The eight warps split each chunk's reduction (4 r's each) and
+// every lane owns a 4x8 register tile (128 FFMA per 12 LDS.128); the eight partial tiles
+// are summed in a fixed order through shared memory, so results are bit-reproducible run
+// to run.  Operands that are contiguous along the reduction in global memory keep that
+// orientation in shared memory, XOR-swizzled at float4 granularity so the strided float4
+// reads are bank-conflict free; ragged / unaligned strips (obs and action widths such as
+// 17, 6, 23) take a zero-filling register path.
 //
 // Why FFMA and not tcgen05 here: a single agent's layer is 256x256x(<=768) -- 64 tiles --
 // and parity is fp32 at 1e-5 (BASELINE.json north_star), which single-pass TF32/BF16
@@ -94,73 +97,78 @@ struct GemmProblem {
 };
 
 constexpr int kTile = 32;
-constexpr int kGemmThreads = 128;
-
-__device__ __forceinline__ int swz(int r, int c) { return r * kTile + (c ^ (((r >> 2) & 7) << 2)); }
+constexpr int kGemmThreads = 256;
+constexpr int kStages = 3;
+constexpr int kTileElems = kTile * kTile;
 
 __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-// load a 4-wide strip along the CONTIGUOUS direction of a global operand, zero filled
-__device__ __forceinline__ float4 load_strip(const float* row_ptr, int pos, int limit, bool row_ok) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (!row_ok || pos >= limit) return v;
-  const float* p = row_ptr + pos;
-  if (pos + 3 < limit && aligned16(p)) {
-    v = *reinterpret_cast<const float4*>(p);
+// ---- cp.async (LDGSTS) helpers; under host emulation they degrade to plain copies ----
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+#ifdef B200_EMU
+  memcpy(smem_dst, gmem_src, 16);
+#else
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem_src));
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef B200_EMU
+  asm volatile("cp.async.commit_group;\n" ::);
+#endif
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+#ifndef B200_EMU
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+#endif
+}
+
+// A 32x32 operand tile in shared memory, 8 float4 "slots" per 32-float row.
+//   K-major (operand contiguous along the reduction r in global): row = c (output index), slots along r,
+//     XOR-swizzled by (c >> 2) so the per-lane float4 reads along r of 8 different rows hit 8 bank groups.
+//   C-major (operand contiguous along the output index c in global): row = r, slots along c, no swizzle.
+// Either way a thread copies one 16-byte strip per operand per chunk, straight from global with cp.async
+// when the strip is complete and 16-byte aligned, else through registers with zero fill.
+template <bool KMAJOR>
+__device__ __forceinline__ void stage_operand(float* tile, const float* base, int ld, int c0, int cmax, int r0, int rlen, int tid) {
+  const int row = tid >> 3, s = tid & 7;
+  float* dst;
+  const float* src;
+  int pos, limit;
+  bool row_ok;
+  if (KMAJOR) {
+    dst = tile + row * kTile + ((s ^ ((row >> 2) & 7)) << 2);
+    row_ok = (c0 + row) < cmax;
+    pos = r0 + (s << 2);
+    limit = rlen;
+    src = base + (long long)(c0 + row) * ld + pos;
   } else {
-    v.x = p[0];
-    if (pos + 1 < limit) v.y = p[1];
-    if (pos + 2 < limit) v.z = p[2];
-    if (pos + 3 < limit) v.w = p[3];
+    dst = tile + row * kTile + (s << 2);
+    row_ok = (r0 + row) < rlen;
+    pos = c0 + (s << 2);
+    limit = cmax;
+    src = base + (long long)(r0 + row) * ld + pos;
   }
-  return v;
-}
-
-// operand element (c, r): RC layout = r contiguous, CC layout = c contiguous.
-// Each thread moves two float4 strips per operand per chunk.
-template <bool RC>
-__device__ __forceinline__ void operand_fetch(const float* base, int ld, int c0, int cmax, int r0, int rlen, int tid, float4 (&reg)[2]) {
-#pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    int q = tid + kGemmThreads * t;
-    if (RC) {
-      int c = q >> 3, r4 = (q & 7) << 2;
-      bool ok = (c0 + c) < cmax;
-      reg[t] = load_strip(base + (long long)(c0 + c) * ld, r0 + r4, rlen, ok);
-    } else {
-      int r = q >> 3, c4 = (q & 7) << 2;
-      bool ok = (r0 + r) < rlen;
-      reg[t] = load_strip(base + (long long)(r0 + r) * ld, c0 + c4, cmax, ok);
+  if (row_ok && pos + 3 < limit && aligned16(src)) {
+    cp_async16(dst, src);
+  } else {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row_ok && pos < limit) {
+      v.x = src[0];
+      if (pos + 1 < limit) v.y = src[1];
+      if (pos + 2 < limit) v.z = src[2];
+      if (pos + 3 < limit) v.w = src[3];
     }
+    *reinterpret_cast<float4*>(dst) = v;
   }
 }
 
-template <bool RC>
-__device__ __forceinline__ void operand_stash(float* tile, int tid, const float4 (&reg)[2]) {
-#pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    int q = tid + kGemmThreads * t;
-    if (RC) {
-      int c = q >> 3, r4 = (q & 7) << 2;
-      tile[swz(r4 + 0, c)] = reg[t].x;
-      tile[swz(r4 + 1, c)] = reg[t].y;
-      tile[swz(r4 + 2, c)] = reg[t].z;
-      tile[swz(r4 + 3, c)] = reg[t].w;
-    } else {
-      int r = q >> 3, c4 = (q & 7) << 2;
-      *reinterpret_cast<float4*>(&tile[swz(r, c4)]) = reg[t];
-    }
-  }
-}
-
-__device__ __forceinline__ void ones_fetch(int c0, int r0, int rlen, int tid, float4 (&reg)[2]) {
-#pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    int q = tid + kGemmThreads * t;
-    int r = q >> 3, c4 = (q & 7) << 2;
-    float one = ((r0 + r) < rlen && (c0 + c4) == 0) ? 1.f : 0.f;
-    reg[t] = make_float4(one, 0.f, 0.f, 0.f);
-  }
+// bias-gradient problems: B(r, j) = (j == 0)
+__device__ __forceinline__ void stage_ones(float* tile, int c0, int r0, int rlen, int tid) {
+  const int row = tid >> 3, s = tid & 7;
+  const float one = ((r0 + row) < rlen && s == 0 && c0 == 0) ? 1.f : 0.f;
+  *reinterpret_cast<float4*>(tile + row * kTile + (s << 2)) = make_float4(one, 0.f, 0.f, 0.f);
 }
 
 __device__ __forceinline__ float act_forward(float v, int act) {
@@ -184,9 +192,10 @@ __device__ __forceinline__ float act_backward(float h, int act) {
 
 template <int MODE>
 __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmProblem* __restrict__ probs, int nprob) {
-  constexpr bool A_RC = (MODE != kWgrad);
-  constexpr bool B_RC = (MODE == kFwd);
-  __shared__ __align__(16) float smem[4 * kTile * kTile];  // 2 stages x (A,B) tiles; reused for the 4 partial tiles
+  constexpr bool A_KM = (MODE != kWgrad);  // A contiguous along the reduction in global memory
+  constexpr bool B_KM = (MODE == kFwd);
+  // 3 pipeline stages x (A tile, B tile) = 24 KB; the same 32 KB later holds the 8 partial output tiles
+  __shared__ __align__(16) float smem[8 * kTileElems];
   __shared__ GemmProblem sp;
 
   const int tid = threadIdx.x;
@@ -214,97 +223,111 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmProblem* _
 #pragma unroll
     for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
 
-  // flattened (segment, chunk) iteration
-  int seg = 0, r0 = 0;
   int nchunks = 0;
   for (int s = 0; s < sp.nseg; ++s) nchunks += (sp.seg[s].len + kTile - 1) / kTile;
 
-  float4 ra[2], rb[2];
-  auto fetch = [&](int s, int r) {
-    const GemmSeg& sg = sp.seg[s];
-    const float* A = sg.A + (long long)g * sg.a_gs;
-    operand_fetch<A_RC>(A, sg.a_ld, i0, I, r, sg.len, tid, ra);
-    if (sg.b_ones) {
-      ones_fetch(j0, r, sg.len, tid, rb);
-    } else {
-      const float* B = sg.B + (long long)g * sg.b_gs;
-      operand_fetch<B_RC>(B, sg.b_ld, j0, J, r, sg.len, tid, rb);
-    }
-  };
-  auto advance = [&]() {
-    r0 += kTile;
-    if (r0 >= sp.seg[seg].len) { r0 = 0; ++seg; }
+  // producer cursor over the flattened (segment, chunk) sequence
+  int pseg = 0, pr0 = 0;
+  auto issue = [&](int stage) {
+    const GemmSeg& sg = sp.seg[pseg];
+    float* At = smem + stage * 2 * kTileElems;
+    float* Bt = At + kTileElems;
+    stage_operand<A_KM>(At, sg.A + (long long)g * sg.a_gs, sg.a_ld, i0, I, pr0, sg.len, tid);
+    if (sg.b_ones) stage_ones(Bt, j0, pr0, sg.len, tid);
+    else stage_operand<B_KM>(Bt, sg.B + (long long)g * sg.b_gs, sg.b_ld, j0, J, pr0, sg.len, tid);
+    pr0 += kTile;
+    if (pr0 >= sg.len) { pr0 = 0; ++pseg; }
   };
 
-  if (nchunks > 0) {
-    fetch(seg, r0);
-    advance();
-    operand_stash<A_RC>(smem, tid, ra);
-    // a b_ones tile is produced in CC form
-    if (B_RC) operand_stash<true>(smem + kTile * kTile, tid, rb); else operand_stash<false>(smem + kTile * kTile, tid, rb);
-  }
-  __syncthreads();
-  int stage = 0;
-  for (int c = 0; c < nchunks; ++c) {
-    const bool more = (c + 1 < nchunks);
-    if (more) { fetch(seg, r0); advance(); }
-    const float* As = smem + stage * 2 * kTile * kTile;
-    const float* Bs = As + kTile * kTile;
+  // prologue: fill kStages-1 stages
 #pragma unroll
-    for (int rr = 0; rr < 8; ++rr) {
-      const int r = warp * 8 + rr;
-      const float4 a4 = *reinterpret_cast<const float4*>(&As[swz(r, li * 4)]);
-      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[swz(r, lj * 8)]);
-      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[swz(r, lj * 8 + 4)]);
-      const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  for (int s = 0; s < kStages - 1; ++s) {
+    if (s < nchunks) issue(s);
+    cp_async_commit();
+  }
+
+  for (int c = 0; c < nchunks; ++c) {
+    cp_async_wait<kStages - 2>();  // chunk c has landed (for this thread's copies)
+    __syncthreads();               // ... and for everybody's; also: stage (c-1)%3 is no longer being read
+    if (c + kStages - 1 < nchunks) issue((c + kStages - 1) % kStages);
+    cp_async_commit();
+
+    const float* As = smem + (c % kStages) * 2 * kTileElems;
+    const float* Bs = As + kTileElems;
+    float av[4][4], bv[8][4];  // [output index][r within this warp's 4-slice]
+    if (A_KM) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const float4 v = *reinterpret_cast<const float4*>(&As[(li * 4 + a) * kTile + ((warp ^ li) << 2)]);
+        av[a][0] = v.x; av[a][1] = v.y; av[a][2] = v.z; av[a][3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const float4 v = *reinterpret_cast<const float4*>(&As[(warp * 4 + rr) * kTile + li * 4]);
+        av[0][rr] = v.x; av[1][rr] = v.y; av[2][rr] = v.z; av[3][rr] = v.w;
+      }
+    }
+    if (B_KM) {
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const int col = lj * 8 + b;
+        const float4 v = *reinterpret_cast<const float4*>(&Bs[col * kTile + ((warp ^ ((col >> 2) & 7)) << 2)]);
+        bv[b][0] = v.x; bv[b][1] = v.y; bv[b][2] = v.z; bv[b][3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const float4 v0 = *reinterpret_cast<const float4*>(&Bs[(warp * 4 + rr) * kTile + lj * 8]);
+        const float4 v1 = *reinterpret_cast<const float4*>(&Bs[(warp * 4 + rr) * kTile + lj * 8 + 4]);
+        bv[0][rr] = v0.x; bv[1][rr] = v0.y; bv[2][rr] = v0.z; bv[3][rr] = v0.w;
+        bv[4][rr] = v1.x; bv[5][rr] = v1.y; bv[6][rr] = v1.z; bv[7][rr] = v1.w;
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
-    }
-    if (more) {
-      float* An = smem + (stage ^ 1) * 2 * kTile * kTile;
-      operand_stash<A_RC>(An, tid, ra);
-      if (B_RC) operand_stash<true>(An + kTile * kTile, tid, rb); else operand_stash<false>(An + kTile * kTile, tid, rb);
-    }
-    __syncthreads();
-    stage ^= 1;
+        for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(av[a][rr], bv[b][rr], acc[a][b]);
   }
+  cp_async_wait<0>();
+  __syncthreads();  // everyone is done reading the pipeline stages: reuse the memory for the partial tiles
 
-  // ---- cross-warp reduction of the four K-slices (fixed order) ----
-  float* part = smem;  // [4][32][32]
+  // ---- cross-warp reduction of the eight K-slices, fixed order (bit-reproducible) ----
+  // partial tile layout: [warp][row][8 slots of float4], slot index XOR (row >> 2) to spread banks
+  float* part = smem;
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
-    float* row = part + warp * kTile * kTile + (li * 4 + a) * kTile + lj * 8;
-    *reinterpret_cast<float4*>(row) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
-    *reinterpret_cast<float4*>(row + 4) = make_float4(acc[a][4], acc[a][5], acc[a][6], acc[a][7]);
+    const int row = li * 4 + a;
+    float* base = part + warp * kTileElems + row * kTile;
+    *reinterpret_cast<float4*>(base + (((2 * lj) ^ li) << 2)) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+    *reinterpret_cast<float4*>(base + (((2 * lj + 1) ^ li) << 2)) = make_float4(acc[a][4], acc[a][5], acc[a][6], acc[a][7]);
   }
   __syncthreads();
-  const int oi = tid >> 2, ojb = (tid & 3) * 8;
-  float out[8];
+  const int oi = tid >> 3, oslot = tid & 7;
+  float out[4];
   {
-    const float* p0 = part + oi * kTile + ojb;
+    const float* p0 = part + oi * kTile + ((oslot ^ ((oi >> 2) & 7)) << 2);
+    float4 s = *reinterpret_cast<const float4*>(p0);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float s = p0[e];
-      s += p0[kTile * kTile + e];
-      s += p0[2 * kTile * kTile + e];
-      s += p0[3 * kTile * kTile + e];
-      out[e] = s;
+    for (int w = 1; w < 8; ++w) {
+      const float4 v = *reinterpret_cast<const float4*>(p0 + w * kTileElems);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
+    out[0] = s.x; out[1] = s.y; out[2] = s.z; out[3] = s.w;
   }
   const int gi = i0 + oi;
   if (gi >= I) return;
-  const int gj0 = j0 + ojb;
+  const int gj0 = j0 + oslot * 4;
   if (gj0 >= J) return;
-  const int nvalid = min(8, J - gj0);
+  const int nvalid = min(4, J - gj0);
 
   if (MODE == kFwd) {
     const float* bias = sp.bias ? sp.bias + (long long)g * sp.bias_gs : nullptr;
     const float* noise = (sp.act == kActTanhNoise) ? sp.aux + (long long)g * sp.aux_gs + (long long)gi * sp.aux_ld : nullptr;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
+    for (int e = 0; e < 4; ++e) {
       if (e < nvalid) {
         float v = out[e] + (bias ? bias[gj0 + e] : 0.f);
         v = act_forward(v, sp.act);
@@ -319,7 +342,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmProblem* _
     float* Cg = sp.C + (long long)g * sp.c_gs + (long long)gi * sp.c_ld;
     const float* H = sp.aux ? sp.aux + (long long)g * sp.aux_gs + (long long)gi * sp.aux_ld : nullptr;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
+    for (int e = 0; e < 4; ++e) {
       if (e < nvalid) {
         float v = out[e];
         if (sp.accumulate) v += Cg[gj0 + e];
@@ -334,7 +357,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmProblem* _
       float* Mp = sp.M + (long long)g * sp.p_gs + (long long)gi * sp.p_ld;
       float* Vp = sp.V + (long long)g * sp.p_gs + (long long)gi * sp.p_ld;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
+      for (int e = 0; e < 4; ++e) {
         if (e < nvalid) {
           float p = Pp[gj0 + e], m = Mp[gj0 + e], v = Vp[gj0 + e];
           adam_update(out[e], p, m, v, s);
@@ -347,12 +370,11 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmProblem* _
     if (!sp.C) return;
   }
   float* Crow = sp.C + (long long)g * sp.c_gs + (long long)gi * sp.c_ld + gj0;
-  if (nvalid == 8 && aligned16(Crow)) {
+  if (nvalid == 4 && aligned16(Crow)) {
     *reinterpret_cast<float4*>(Crow) = make_float4(out[0], out[1], out[2], out[3]);
-    *reinterpret_cast<float4*>(Crow + 4) = make_float4(out[4], out[5], out[6], out[7]);
   } else {
 #pragma unroll
-    for (int e = 0; e < 8; ++e)
+    for (int e = 0; e < 4; ++e)
       if (e < nvalid) Crow[e] = out[e];
   }
 }

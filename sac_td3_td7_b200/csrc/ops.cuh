@@ -79,6 +79,8 @@ struct StepState {
   int adam_t[4];      // step count per optimizer
   int info_slot;      // ring slot the loss kernels of the current step write to
   int pad[2];
+  double b1pow[4];    // beta1^t, beta2^t per optimizer, carried as running products (1.0 at t = 0)
+  double b2pow[4];
 };
 
 // one thread: advance counters and refresh the Adam scalars of the optimizers that step now
@@ -90,8 +92,10 @@ __global__ void prep_step_kernel(StepState* st, AdamScalars* adam, const OptimHy
     if (!((step_mask >> k) & 1u)) continue;
     const int t = ++st->adam_t[k];
     const OptimHyper h = hyper[k];
-    const double bc1 = 1.0 - pow(h.beta1, (double)t);
-    const double bc2 = 1.0 - pow(h.beta2, (double)t);
+    st->b1pow[k] *= h.beta1;
+    st->b2pow[k] *= h.beta2;
+    const double bc1 = 1.0 - st->b1pow[k];
+    const double bc2 = 1.0 - st->b2pow[k];
     AdamScalars s;
     s.w1 = (float)(1.0 - h.beta1);
     s.beta2 = (float)h.beta2;
@@ -182,15 +186,36 @@ __device__ __forceinline__ float block_min_256(float v, float* red) { return -bl
 // ----------------------------------------------------------------------------- LAP priority write-back
 // priority[idx[b]] = prio[b]; duplicates: the LAST batch position wins (numpy/torch index
 // assignment); running max via atomicMax on the (positive) float bits.
+// Duplicates are resolved with a small open-addressing hash table in shared memory
+// (key = row index, value = highest batch position that sampled it): O(1) per thread.
+constexpr int kScatterSlots = 2048;  // >= 2 * max batch (1024)
+struct ScatterTable {
+  unsigned long long keys[kScatterSlots];
+  int last[kScatterSlots];
+};
+__device__ __forceinline__ size_t scatter_smem_bytes() { return sizeof(ScatterTable); }
+
 __device__ __forceinline__ void lap_scatter_block(float* __restrict__ priority, float* __restrict__ max_priority,
-                                                  const long long* __restrict__ idx, float p, int b, int B, long long* sh_idx /*[B]*/) {
-  long long my = -1;
-  if (b < B) { my = idx[b]; sh_idx[b] = my; }
+                                                  const long long* __restrict__ idx, float p, int b, int B, ScatterTable* tab) {
+  const unsigned long long kEmpty = ~0ULL;
+  for (int i = threadIdx.x; i < kScatterSlots; i += blockDim.x) { tab->keys[i] = kEmpty; tab->last[i] = -1; }
+  __syncthreads();
+  unsigned long long my = 0;
+  int slot = -1;
+  if (b < B) {
+    my = (unsigned long long)idx[b];
+    unsigned h = (unsigned)((my * 0x9E3779B97F4A7C15ULL) >> 40) & (kScatterSlots - 1);
+    for (;;) {
+      const unsigned long long old = atomicCAS(&tab->keys[h], kEmpty, my);
+      if (old == kEmpty || old == my) break;
+      h = (h + 1) & (kScatterSlots - 1);
+    }
+    slot = (int)h;
+    atomicMax(&tab->last[slot], b);
+  }
   __syncthreads();
   if (b < B) {
-    bool last = true;
-    for (int k = b + 1; k < B; ++k) if (sh_idx[k] == my) { last = false; break; }
-    if (last) priority[my] = p;
+    if (tab->last[slot] == b) priority[my] = p;
     atomicMax(reinterpret_cast<int*>(max_priority), __float_as_int(p));
   }
 }
@@ -266,7 +291,7 @@ struct CriticLossArgs {
 
 __global__ void __launch_bounds__(1024) critic_loss_kernel(CriticLossArgs a) {
   __shared__ float red[32];
-  B200_DYN_SMEM(long long, sh_idx);  // [B] sampled indices, for the last-writer-wins scatter
+  B200_DYN_SMEM(ScatterTable, scatter_tab);  // hash table for the last-writer-wins scatter
   const int g = blockIdx.x;
   const int b = threadIdx.x;
   const int B = a.B;
@@ -315,10 +340,10 @@ __global__ void __launch_bounds__(1024) critic_loss_kernel(CriticLossArgs a) {
   const float tot = block_sum_256(l, red);
   if (b == 0) a.info[g * a.info_gs + (long long)a.st->info_slot * a.info_stride + a.info_col] = tot * invB;
   if (a.use_lap) {
-    const float p = (b < B) ? (float)pow((double)fmaxf(fmaxf(td1, td2), 1.0f), 0.4) : 0.f;
+    const float p = (b < B) ? powf(fmaxf(fmaxf(td1, td2), 1.0f), 0.4f) : 0.f;
     if (a.prio_out && b < B) a.prio_out[o + b] = p;
     if (a.priority) {
-      lap_scatter_block(a.priority + g * a.prio_gs, a.max_priority + g, a.idx + g * a.idx_gs, p, b, B, sh_idx);
+      lap_scatter_block(a.priority + g * a.prio_gs, a.max_priority + g, a.idx + g * a.idx_gs, p, b, B, scatter_tab);
     }
   }
 }

@@ -79,19 +79,22 @@ __global__ void __launch_bounds__(256) lap_sample_kernel(SampleArgs a) {
   const int size = a.size;
 
   if (a.prioritized) {
+    // inclusive scan of the tile sums in shared memory: coalesced copy in, per-thread serial scan of
+    // a contiguous run, warp/block scan of the run totals, add the offsets back
     const int nt = a.ntiles;
     const double* ts = a.tile_sums + (long long)g * a.ts_gs;
+    for (int t = tid; t < nt; t += 256) prefix[t] = ts[t];
+    __syncthreads();
     const int per = (nt + 255) / 256;
     const int lo = min(tid * per, nt), hi = min(lo + per, nt);
     double local = 0.0;
-    for (int t = lo; t < hi; ++t) local += ts[t];
-    double incl = warp_inclusive_scan(local, lane);
+    for (int t = lo; t < hi; ++t) { local += prefix[t]; prefix[t] = local; }
+    const double incl = warp_inclusive_scan(local, lane);
     if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    double off = 0.0;
+    double off = incl - local;
     for (int w = 0; w < warp; ++w) off += warp_tot[w];
-    double run = off + incl - local;
-    for (int t = lo; t < hi; ++t) { run += ts[t]; prefix[t] = run; }
+    for (int t = lo; t < hi; ++t) prefix[t] += off;
     __syncthreads();
   }
 
@@ -186,10 +189,10 @@ __global__ void __launch_bounds__(256) lap_sample_kernel(SampleArgs a) {
 __global__ void __launch_bounds__(1024) lap_update_priority_kernel(float* __restrict__ priority, long long prio_gs, float* __restrict__ max_priority,
                                                                    const long long* __restrict__ idx, long long idx_gs, const float* __restrict__ prio,
                                                                    long long p_gs, int B) {
-  B200_DYN_SMEM(long long, sh_idx);
+  B200_DYN_SMEM(ScatterTable, tab);
   const int g = blockIdx.x, b = threadIdx.x;
   const float p = (b < B) ? prio[(long long)g * p_gs + b] : 0.f;
-  lap_scatter_block(priority + (long long)g * prio_gs, max_priority + g, idx + (long long)g * idx_gs, p, b, B, sh_idx);
+  lap_scatter_block(priority + (long long)g * prio_gs, max_priority + g, idx + (long long)g * idx_gs, p, b, B, tab);
 }
 
 __global__ void __launch_bounds__(256) lap_max_kernel(const float* __restrict__ priority, long long prio_gs, int size, float* __restrict__ max_priority) {
@@ -338,7 +341,7 @@ struct Replay {
     B200_REQUIRE(prioritized, "update_priority on a uniform buffer");
     B200_REQUIRE(B == last_batch, "update_priority: batch size differs from the last sample()");
     dim3 grid((unsigned)groups), block((unsigned)round_up(B, 32));
-    B200_LAUNCH(lap_update_priority_kernel, grid, block, (size_t)B * sizeof(long long), stream, d_priority, cap_pad, d_max_priority, d_idx,
+    B200_LAUNCH(lap_update_priority_kernel, grid, block, sizeof(ScatterTable), stream, d_priority, cap_pad, d_max_priority, d_idx,
                 (long long)max_batch, prio_dev, p_gs, B);
     B200_CHECK_LAUNCH();
     return kOk;

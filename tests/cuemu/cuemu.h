@@ -374,6 +374,10 @@ static inline unsigned atomicCAS(unsigned* a, unsigned cmp, unsigned v) {
   __atomic_compare_exchange_n(a, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
   return cmp;
 }
+static inline unsigned long long atomicCAS(unsigned long long* a, unsigned long long cmp, unsigned long long v) {
+  __atomic_compare_exchange_n(a, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+  return cmp;
+}
 static inline unsigned atomicInc(unsigned* a, unsigned lim) {
   unsigned old = __atomic_load_n(a, __ATOMIC_SEQ_CST);
   for (;;) {
