@@ -198,7 +198,7 @@ def gemm_roofline(lib, torch, S, A, groups=1):
     add([qn, zsa, zs], H)      # q2.q1
     arr = (_lib.GemmProblem * len(probs))(*probs)
     ms = C.c_float()
-    _lib.check(lib.b200rl_op_gemm_timed(0, arr, len(probs), groups, 20, 200, C.byref(ms), torch.cuda.current_stream().cuda_stream))
+    _lib.check(lib.b200rl_op_gemm_timed(0, arr, len(probs), groups, int(os.environ.get("B200_GEMM_WARMUP", "20")), int(os.environ.get("B200_GEMM_ITERS", "200")), C.byref(ms), torch.cuda.current_stream().cuda_stream))
     return flops, ms.value
 
 

@@ -98,7 +98,7 @@ struct MlpAgent : AgentBase {
   template <class V>
   int up(GemmTable& t, int mode, V probs) {
     std::vector<GemmProblem> v(probs);
-    return gemm_table_upload(&t, mode, v, &arena);
+    return gemm_table_upload(&t, mode, v, &arena, G);
   }
 
   int build_tables() {

@@ -112,7 +112,7 @@ struct TD7Agent : AgentBase {
   template <class V>
   int up(GemmTable& t, int mode, V probs) {
     std::vector<GemmProblem> v(probs);
-    return gemm_table_upload(&t, mode, v, &arena);
+    return gemm_table_upload(&t, mode, v, &arena, G);
   }
   int upn(RowTable& t, bool bwd, std::vector<RowOp> ops) { return row_table_upload(&t, bwd, ops, &arena); }
   static RowOp nf(const Mat& x, const Mat& y) { return make_rowop(x.p, x.ld, x.gs, y.p, y.ld, y.gs, x.rows, x.cols); }

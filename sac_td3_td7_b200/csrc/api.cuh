@@ -202,7 +202,7 @@ static int build_act_path(b200rl_agent* h) {
   auto mk = [&](int cols) { Mat m; m.p = base + cur; m.rows = 1; m.cols = cols; m.ld = cols; m.gs = per; cur += round_up(cols, 4); return m; };
   h->o_s = mk(S); h->ah1 = mk(H); h->ah2 = mk(H); h->ap0 = mk(H); h->ap0n = mk(H);
   h->au3 = mk(Z > 0 ? Z : 4); h->azs = mk(Z > 0 ? Z : 4); h->ap1 = mk(H); h->ap2 = mk(H); h->aout = mk(Aout);
-  auto up = [&](GemmTable& t, PV v) { return gemm_table_upload(&t, kFwd, v, &a.arena); };
+  auto up = [&](GemmTable& t, PV v) { return gemm_table_upload(&t, kFwd, v, &a.arena, a.G); };
   if (h->td7) {
     TD7Agent& t = *h->td7;
     B200_TRY(up(h->act_t[0], PV{fwd_problem(t.fe, 0, {h->o_s}, h->ah1, kActElu), fwd_problem(t.pol, 0, {h->o_s}, h->ap0, kActNone)}));
@@ -534,7 +534,7 @@ int b200rl_op_gemm(int mode, const b200rl_gemm_problem* problems_host, int nprob
   memcpy(v.data(), problems_host, (size_t)nproblems * sizeof(GemmProblem));
   DeviceArena tmp;
   GemmTable t;
-  B200_TRY(gemm_table_upload(&t, mode, v, &tmp));
+  B200_TRY(gemm_table_upload(&t, mode, v, &tmp, groups));
   B200_TRY(gemm_table_launch(t, groups, as_stream(stream)));
   B200_CHECK_CUDA(cudaStreamSynchronize(as_stream(stream)));
   return kOk;
@@ -547,7 +547,7 @@ int b200rl_op_gemm_timed(int mode, const b200rl_gemm_problem* problems_host, int
   memcpy(v.data(), problems_host, (size_t)nproblems * sizeof(GemmProblem));
   DeviceArena tmp;
   GemmTable t;
-  B200_TRY(gemm_table_upload(&t, mode, v, &tmp));
+  B200_TRY(gemm_table_upload(&t, mode, v, &tmp, groups));
   cudaStream_t s = as_stream(stream);
   for (int i = 0; i < warmup; ++i) B200_TRY(gemm_table_launch(t, groups, s));
 #ifndef B200_EMU

@@ -96,12 +96,41 @@ struct GemmProblem {
   int tiles_j;
 };
 
-constexpr int kTile = 32;
+// One launch: the problem table travels in kernel-parameter (constant) memory, so a CTA finds its
+// problem without a dependent global load.  With splitk > 1 every output tile is computed by `splitk`
+// CTAs, each over a contiguous slice of the reduction chunks; the partial tiles meet in `scratch` and the
+// CTA that arrives last (ticket counter) sums them in split order -- so the result does not depend on
+// arrival order -- and runs the epilogue.  Splitting is what gives a single agent's 64-tile layers
+// enough CTAs to occupy the machine and cuts the serial chunk chain per CTA.
+constexpr int kMaxProblems = 24;
+struct GemmLaunch {
+  GemmProblem p[kMaxProblems];
+  int nprob;
+  int splitk;
+  int total_tiles;
+  int pad;
+  float* scratch;      // [groups][total_tiles][splitk][32*32]
+  unsigned* tickets;   // [groups][total_tiles], zero between launches
+};
+
+constexpr int kTile = 32;   // output tile edge
+constexpr int kBK = 64;     // reduction depth of one pipeline stage
 constexpr int kGemmThreads = 256;
 constexpr int kStages = 3;
-constexpr int kTileElems = kTile * kTile;
+constexpr int kTileElems = kTile * kTile;          // one partial output tile
+constexpr int kStageElems = 2 * kTile * kBK;       // A tile + B tile of one stage
+constexpr int kGemmSmemBytes = kStages * kStageElems * (int)sizeof(float);  // 48 KB (>= 8 partial tiles = 32 KB)
 
 __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// L2-coherent 128-bit load (bypasses the non-coherent L1): data written by other CTAs of this launch
+__device__ __forceinline__ float4 ld_cg_f4(const float* p) {
+#ifdef B200_EMU
+  return *reinterpret_cast<const float4*>(p);
+#else
+  return __ldcg(reinterpret_cast<const float4*>(p));
+#endif
+}
 
 // ---- cp.async (LDGSTS) helpers; under host emulation they degrade to plain copies ----
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
@@ -124,51 +153,97 @@ __device__ __forceinline__ void cp_async_wait() {
 #endif
 }
 
-// A 32x32 operand tile in shared memory, 8 float4 "slots" per 32-float row.
-//   K-major (operand contiguous along the reduction r in global): row = c (output index), slots along r,
-//     XOR-swizzled by (c >> 2) so the per-lane float4 reads along r of 8 different rows hit 8 bank groups.
-//   C-major (operand contiguous along the output index c in global): row = r, slots along c, no swizzle.
-// Either way a thread copies one 16-byte strip per operand per chunk, straight from global with cp.async
-// when the strip is complete and 16-byte aligned, else through registers with zero fill.
+// One operand of one reduction segment, as seen by one thread: the two 16-byte strips it copies per
+// chunk.  Shared-memory tile layouts (32 output indices x 64 reduction indices):
+//   K-major (operand contiguous along the reduction r in global): row = c, 16 float4 slots along r,
+//     slot index XOR (c >> 2) & 7 so the strided per-lane float4 reads hit 8 distinct bank groups;
+//   C-major (operand contiguous along the output index c in global): row = r, 8 float4 slots along c.
+// Everything that does not change from chunk to chunk (row validity, alignment, base pointers, the
+// shared-memory offset) is computed once per segment; per chunk the fast path is one bounds test,
+// one cp.async and one pointer bump per strip.
 template <bool KMAJOR>
-__device__ __forceinline__ void stage_operand(float* tile, const float* base, int ld, int c0, int cmax, int r0, int rlen, int tid) {
-  const int row = tid >> 3, s = tid & 7;
-  float* dst;
-  const float* src;
-  int pos, limit;
-  bool row_ok;
-  if (KMAJOR) {
-    dst = tile + row * kTile + ((s ^ ((row >> 2) & 7)) << 2);
-    row_ok = (c0 + row) < cmax;
-    pos = r0 + (s << 2);
-    limit = rlen;
-    src = base + (long long)(c0 + row) * ld + pos;
-  } else {
-    dst = tile + row * kTile + (s << 2);
-    row_ok = (r0 + row) < rlen;
-    pos = c0 + (s << 2);
-    limit = cmax;
-    src = base + (long long)(r0 + row) * ld + pos;
-  }
-  if (row_ok && pos + 3 < limit && aligned16(src)) {
-    cp_async16(dst, src);
-  } else {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row_ok && pos < limit) {
-      v.x = src[0];
-      if (pos + 1 < limit) v.y = src[1];
-      if (pos + 2 < limit) v.z = src[2];
-      if (pos + 3 < limit) v.w = src[3];
-    }
-    *reinterpret_cast<float4*>(dst) = v;
-  }
-}
+struct OperandCursor {
+  const float* src[2];
+  int dst[2];        // float offset inside the operand tile
+  int pos;           // K-major: r offset of the strip inside the chunk (4*s); C-major: c0 + 4*s
+  int row[2];        // C-major: r offset of the strip inside the chunk
+  bool row_ok[2];    // K-major: output row inside the problem
+  bool fast[2];      // 16-byte aligned source and (C-major) complete strip
+  long long bump;    // pointer advance per chunk
 
-// bias-gradient problems: B(r, j) = (j == 0)
+  __device__ __forceinline__ void init(const float* base, int ld, int c0, int cmax, int tid, int r_start) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (KMAJOR) {
+        const int c = (tid >> 4) + 16 * h, s = tid & 15;
+        dst[h] = c * kBK + ((s ^ ((c >> 2) & 7)) << 2);
+        pos = s << 2;
+        row[h] = 0;
+        row_ok[h] = (c0 + c) < cmax;
+        src[h] = base + (long long)(c0 + c) * ld + pos + r_start;
+        fast[h] = row_ok[h] && aligned16(src[h]);
+        bump = kBK;
+      } else {
+        const int r = (tid >> 3) + 32 * h, s = tid & 7;
+        dst[h] = r * kTile + (s << 2);
+        pos = c0 + (s << 2);
+        row[h] = r;
+        row_ok[h] = true;
+        src[h] = base + (long long)(r_start + r) * ld + pos;
+        fast[h] = (pos + 3 < cmax) && aligned16(src[h]);
+        bump = (long long)kBK * ld;
+      }
+    }
+  }
+  // copy this thread's strips of the chunk starting at reduction offset r0 (segment length rlen)
+  __device__ __forceinline__ void stage(float* tile, int r0, int rlen, int cmax) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float* d = tile + dst[h];
+      if (KMAJOR) {
+        const int p = r0 + pos;
+        if (fast[h] && p + 3 < rlen) {
+          cp_async16(d, src[h]);
+        } else {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row_ok[h] && p < rlen) {
+            const float* q = src[h];
+            v.x = q[0];
+            if (p + 1 < rlen) v.y = q[1];
+            if (p + 2 < rlen) v.z = q[2];
+            if (p + 3 < rlen) v.w = q[3];
+          }
+          *reinterpret_cast<float4*>(d) = v;
+        }
+      } else {
+        const bool in = (r0 + row[h]) < rlen;
+        if (fast[h] && in) {
+          cp_async16(d, src[h]);
+        } else {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (in && pos < cmax) {
+            const float* q = src[h];
+            v.x = q[0];
+            if (pos + 1 < cmax) v.y = q[1];
+            if (pos + 2 < cmax) v.z = q[2];
+            if (pos + 3 < cmax) v.w = q[3];
+          }
+          *reinterpret_cast<float4*>(d) = v;
+        }
+      }
+      src[h] += bump;
+    }
+  }
+};
+
+// bias-gradient problems: B(r, j) = (j == 0)   (C-major tile)
 __device__ __forceinline__ void stage_ones(float* tile, int c0, int r0, int rlen, int tid) {
-  const int row = tid >> 3, s = tid & 7;
-  const float one = ((r0 + row) < rlen && s == 0 && c0 == 0) ? 1.f : 0.f;
-  *reinterpret_cast<float4*>(tile + row * kTile + (s << 2)) = make_float4(one, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int r = (tid >> 3) + 32 * h, s = tid & 7;
+    const float one = ((r0 + r) < rlen && s == 0 && c0 == 0) ? 1.f : 0.f;
+    *reinterpret_cast<float4*>(tile + r * kTile + (s << 2)) = make_float4(one, 0.f, 0.f, 0.f);
+  }
 }
 
 __device__ __forceinline__ float act_forward(float v, int act) {
@@ -191,25 +266,22 @@ __device__ __forceinline__ float act_backward(float h, int act) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmProblem* __restrict__ probs, int nprob) {
+__global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_constant__ GemmLaunch L) {
   constexpr bool A_KM = (MODE != kWgrad);  // A contiguous along the reduction in global memory
   constexpr bool B_KM = (MODE == kFwd);
-  // 3 pipeline stages x (A tile, B tile) = 24 KB; the same 32 KB later holds the 8 partial output tiles
-  __shared__ __align__(16) float smem[8 * kTileElems];
-  __shared__ GemmProblem sp;
+  // 3 pipeline stages x (A tile 32x64, B tile 32x64) = 48 KB; the first 32 KB later hold the 8 partial tiles
+  B200_DYN_SMEM(float, smem);
+  __shared__ unsigned s_ticket;
 
   const int tid = threadIdx.x;
   const int g = blockIdx.y;
-  {
-    int pi = 0;
-    const int tile_id = blockIdx.x;
-    while (pi + 1 < nprob && tile_id >= probs[pi + 1].tile_begin) ++pi;
-    const int* src = reinterpret_cast<const int*>(&probs[pi]);
-    int* dst = reinterpret_cast<int*>(&sp);
-    for (int w = tid; w < (int)(sizeof(GemmProblem) / sizeof(int)); w += kGemmThreads) dst[w] = src[w];
-  }
-  __syncthreads();
-  const int t_local = (int)blockIdx.x - sp.tile_begin;
+  const int splitk = L.splitk;
+  const int tile_id = (int)blockIdx.x / splitk;
+  const int split = (int)blockIdx.x - tile_id * splitk;
+  int pi = 0;
+  while (pi + 1 < L.nprob && tile_id >= L.p[pi + 1].tile_begin) ++pi;
+  const GemmProblem& sp = L.p[pi];
+  const int t_local = tile_id - sp.tile_begin;
   const int i0 = (t_local / sp.tiles_j) * kTile;
   const int j0 = (t_local % sp.tiles_j) * kTile;
   const int I = sp.I, J = sp.J;
@@ -223,21 +295,45 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmProblem* _
 #pragma unroll
     for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
 
-  int nchunks = 0;
-  for (int s = 0; s < sp.nseg; ++s) nchunks += (sp.seg[s].len + kTile - 1) / kTile;
+  int total_chunks = 0;
+  for (int s = 0; s < sp.nseg; ++s) total_chunks += (sp.seg[s].len + kBK - 1) / kBK;
+  // this CTA's slice of the flattened (segment, chunk) sequence
+  const int per_split = (total_chunks + splitk - 1) / splitk;
+  const int c_begin = min(split * per_split, total_chunks);
+  const int nchunks = min(c_begin + per_split, total_chunks) - c_begin;
 
-  // producer cursor over the flattened (segment, chunk) sequence
-  int pseg = 0, pr0 = 0;
-  auto issue = [&](int stage) {
+  // producer cursor
+  OperandCursor<A_KM> ca;
+  OperandCursor<B_KM> cb;
+  int pseg = 0, pr0 = 0, plen = 0;
+  bool ones = false;
+  auto open_segment = [&](int r_start) {
     const GemmSeg& sg = sp.seg[pseg];
-    float* At = smem + stage * 2 * kTileElems;
-    float* Bt = At + kTileElems;
-    stage_operand<A_KM>(At, sg.A + (long long)g * sg.a_gs, sg.a_ld, i0, I, pr0, sg.len, tid);
-    if (sg.b_ones) stage_ones(Bt, j0, pr0, sg.len, tid);
-    else stage_operand<B_KM>(Bt, sg.B + (long long)g * sg.b_gs, sg.b_ld, j0, J, pr0, sg.len, tid);
-    pr0 += kTile;
-    if (pr0 >= sg.len) { pr0 = 0; ++pseg; }
+    plen = sg.len;
+    ones = sg.b_ones != 0;
+    ca.init(sg.A + (long long)g * sg.a_gs, sg.a_ld, i0, I, tid, r_start);
+    if (!ones) cb.init(sg.B + (long long)g * sg.b_gs, sg.b_ld, j0, J, tid, r_start);
+    pr0 = r_start;
   };
+  auto issue = [&](int stage) {
+    float* At = smem + stage * kStageElems;
+    float* Bt = At + kTile * kBK;
+    ca.stage(At, pr0, plen, I);
+    if (ones) stage_ones(Bt, j0, pr0, plen, tid);
+    else cb.stage(Bt, pr0, plen, J);
+    pr0 += kBK;
+    if (pr0 >= plen && ++pseg < sp.nseg) open_segment(0);
+  };
+  if (nchunks > 0) {
+    int skip = c_begin;  // walk to the segment that holds chunk c_begin
+    for (;;) {
+      const int sc = (sp.seg[pseg].len + kBK - 1) / kBK;
+      if (skip < sc) break;
+      skip -= sc;
+      ++pseg;
+    }
+    open_segment(skip * kBK);
+  }
 
   // prologue: fill kStages-1 stages
 #pragma unroll
@@ -247,49 +343,53 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmProblem* _
   }
 
   for (int c = 0; c < nchunks; ++c) {
-    cp_async_wait<kStages - 2>();  // chunk c has landed (for this thread's copies)
-    __syncthreads();               // ... and for everybody's; also: stage (c-1)%3 is no longer being read
+    cp_async_wait<kStages - 2>();  // chunk c has landed (this thread's copies)
+    __syncthreads();               // ... and everybody's; also: the stage refilled below is no longer being read
     if (c + kStages - 1 < nchunks) issue((c + kStages - 1) % kStages);
     cp_async_commit();
 
-    const float* As = smem + (c % kStages) * 2 * kTileElems;
-    const float* Bs = As + kTileElems;
-    float av[4][4], bv[8][4];  // [output index][r within this warp's 4-slice]
-    if (A_KM) {
+    const float* As = smem + (c % kStages) * kStageElems;
+    const float* Bs = As + kTile * kBK;
+    // this warp's 8 reduction indices of the chunk: r = 8*warp .. 8*warp+7, in two halves of 4
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const float4 v = *reinterpret_cast<const float4*>(&As[(li * 4 + a) * kTile + ((warp ^ li) << 2)]);
-        av[a][0] = v.x; av[a][1] = v.y; av[a][2] = v.z; av[a][3] = v.w;
-      }
-    } else {
+    for (int h = 0; h < 2; ++h) {
+      float av[4][4], bv[8][4];  // [output index][r within the half]
+      if (A_KM) {
 #pragma unroll
-      for (int rr = 0; rr < 4; ++rr) {
-        const float4 v = *reinterpret_cast<const float4*>(&As[(warp * 4 + rr) * kTile + li * 4]);
-        av[0][rr] = v.x; av[1][rr] = v.y; av[2][rr] = v.z; av[3][rr] = v.w;
+        for (int a = 0; a < 4; ++a) {
+          const float4 v = *reinterpret_cast<const float4*>(&As[(li * 4 + a) * kBK + (((2 * warp + h) ^ li) << 2)]);
+          av[a][0] = v.x; av[a][1] = v.y; av[a][2] = v.z; av[a][3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const float4 v = *reinterpret_cast<const float4*>(&As[(warp * 8 + h * 4 + rr) * kTile + li * 4]);
+          av[0][rr] = v.x; av[1][rr] = v.y; av[2][rr] = v.z; av[3][rr] = v.w;
+        }
       }
+      if (B_KM) {
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          const int col = lj * 8 + b;
+          const float4 v = *reinterpret_cast<const float4*>(&Bs[col * kBK + (((2 * warp + h) ^ ((col >> 2) & 7)) << 2)]);
+          bv[b][0] = v.x; bv[b][1] = v.y; bv[b][2] = v.z; bv[b][3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const float4 v0 = *reinterpret_cast<const float4*>(&Bs[(warp * 8 + h * 4 + rr) * kTile + lj * 8]);
+          const float4 v1 = *reinterpret_cast<const float4*>(&Bs[(warp * 8 + h * 4 + rr) * kTile + lj * 8 + 4]);
+          bv[0][rr] = v0.x; bv[1][rr] = v0.y; bv[2][rr] = v0.z; bv[3][rr] = v0.w;
+          bv[4][rr] = v1.x; bv[5][rr] = v1.y; bv[6][rr] = v1.z; bv[7][rr] = v1.w;
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(av[a][rr], bv[b][rr], acc[a][b]);
     }
-    if (B_KM) {
-#pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        const int col = lj * 8 + b;
-        const float4 v = *reinterpret_cast<const float4*>(&Bs[col * kTile + ((warp ^ ((col >> 2) & 7)) << 2)]);
-        bv[b][0] = v.x; bv[b][1] = v.y; bv[b][2] = v.z; bv[b][3] = v.w;
-      }
-    } else {
-#pragma unroll
-      for (int rr = 0; rr < 4; ++rr) {
-        const float4 v0 = *reinterpret_cast<const float4*>(&Bs[(warp * 4 + rr) * kTile + lj * 8]);
-        const float4 v1 = *reinterpret_cast<const float4*>(&Bs[(warp * 4 + rr) * kTile + lj * 8 + 4]);
-        bv[0][rr] = v0.x; bv[1][rr] = v0.y; bv[2][rr] = v0.z; bv[3][rr] = v0.w;
-        bv[4][rr] = v1.x; bv[5][rr] = v1.y; bv[6][rr] = v1.z; bv[7][rr] = v1.w;
-      }
-    }
-#pragma unroll
-    for (int rr = 0; rr < 4; ++rr)
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(av[a][rr], bv[b][rr], acc[a][b]);
   }
   cp_async_wait<0>();
   __syncthreads();  // everyone is done reading the pipeline stages: reuse the memory for the partial tiles
@@ -316,6 +416,26 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmProblem* _
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
     out[0] = s.x; out[1] = s.y; out[2] = s.z; out[3] = s.w;
+  }
+  if (splitk > 1) {
+    // publish this split's partial tile, take a ticket; the last arriver sums all splits in split order
+    const long long tile_lin = (long long)g * L.total_tiles + tile_id;
+    float* mine = L.scratch + (tile_lin * splitk + split) * kTileElems;
+    *reinterpret_cast<float4*>(mine + tid * 4) = make_float4(out[0], out[1], out[2], out[3]);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(&L.tickets[tile_lin], 1u);
+    __syncthreads();
+    if (s_ticket != (unsigned)(splitk - 1)) return;
+    __threadfence();
+    const float* all = L.scratch + tile_lin * splitk * kTileElems + tid * 4;
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < splitk; ++k) {
+      const float4 v = ld_cg_f4(all + (long long)k * kTileElems);
+      s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+    }
+    out[0] = s4.x; out[1] = s4.y; out[2] = s4.z; out[3] = s4.w;
+    if (tid == 0) L.tickets[tile_lin] = 0u;  // ready for the next launch / graph replay
   }
   const int gi = i0 + oi;
   if (gi >= I) return;
@@ -380,12 +500,14 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmProblem* _
 }
 
 // ----------------------------------------------------------------------------- host side
-// A launch table: problems are appended on the host, uploaded once, then replayed.
+// A launch table: problems are appended on the host once, then replayed (the struct is passed by value
+// as the kernel parameter; scratch / tickets for split-K live in device memory owned by the table).
 struct GemmTable {
-  GemmProblem* d_probs = nullptr;
+  GemmLaunch launch;
   int nprob = 0;
   int total_tiles = 0;
   int mode = kFwd;
+  int groups = 1;
 };
 
 }  // namespace b200rl

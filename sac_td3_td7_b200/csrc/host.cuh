@@ -60,7 +60,23 @@ inline void add_seg(GemmProblem& p, const float* A, int a_ld, long long a_gs, co
   s.b_ones = 0;
 }
 
-inline int gemm_table_upload(GemmTable* t, int mode, std::vector<GemmProblem>& probs, DeviceArena* arena) {
+// choose how many CTAs share one output tile: enough to put ~3 CTAs on each of the 148 SMs, never more
+// than the longest problem has reduction chunks, never when stacked seeds already fill the machine
+inline int choose_splitk(const std::vector<GemmProblem>& probs, int tiles, int groups) {
+  int max_chunks = 1;
+  for (const auto& p : probs) {
+    int c = 0;
+    for (int s = 0; s < p.nseg; ++s) c += ceil_div(p.seg[s].len, kBK);
+    max_chunks = std::max(max_chunks, c);
+  }
+  const long long ctas = (long long)tiles * groups;
+  int s = (int)(444 / std::max<long long>(ctas, 1));
+  s = std::max(1, std::min(s, std::min(max_chunks, 8)));
+  return s;
+}
+
+inline int gemm_table_upload(GemmTable* t, int mode, std::vector<GemmProblem>& probs, DeviceArena* arena, int groups = 1, int force_splitk = 0) {
+  B200_REQUIRE((int)probs.size() <= kMaxProblems, "too many problems in one gemm launch");
   int tiles = 0;
   for (auto& p : probs) {
     B200_REQUIRE(p.nseg >= 1 && p.nseg <= 3, "gemm problem needs 1..3 segments");
@@ -72,18 +88,39 @@ inline int gemm_table_upload(GemmTable* t, int mode, std::vector<GemmProblem>& p
   t->mode = mode;
   t->nprob = (int)probs.size();
   t->total_tiles = tiles;
-  B200_TRY(arena->alloc(&t->d_probs, probs.size()));
-  B200_CHECK_CUDA(cudaMemcpy(t->d_probs, probs.data(), probs.size() * sizeof(GemmProblem), cudaMemcpyHostToDevice));
+  t->groups = groups;
+  memset(&t->launch, 0, sizeof(t->launch));
+  for (size_t i = 0; i < probs.size(); ++i) t->launch.p[i] = probs[i];
+  t->launch.nprob = t->nprob;
+  t->launch.total_tiles = tiles;
+  t->launch.splitk = force_splitk > 0 ? force_splitk : choose_splitk(probs, tiles, groups);
+  if (t->launch.splitk > 1) {
+    B200_TRY(arena->alloc(&t->launch.scratch, (size_t)groups * tiles * t->launch.splitk * kTileElems));
+    B200_TRY(arena->alloc(&t->launch.tickets, (size_t)groups * tiles));
+  }
   return kOk;
 }
 
 inline int gemm_table_launch(const GemmTable& t, int groups, cudaStream_t stream) {
   if (t.nprob == 0) return kOk;
-  dim3 grid((unsigned)t.total_tiles, (unsigned)groups, 1), block(kGemmThreads, 1, 1);
+  if (groups != t.groups) {
+    set_last_error("gemm table launched with a different number of groups than it was built for");
+    return kErrState;
+  }
+  dim3 grid((unsigned)(t.total_tiles * t.launch.splitk), (unsigned)groups, 1), block(kGemmThreads, 1, 1);
+#ifndef B200_EMU
+  static bool attr_set = false;  // 48 KB of dynamic shared memory needs the opt-in once per kernel
+  if (!attr_set) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<kFwd>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<kDgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<kWgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    attr_set = true;
+  }
+#endif
   switch (t.mode) {
-    case kFwd: { auto k = gemm_kernel<kFwd>; B200_LAUNCH(k, grid, block, 0, stream, t.d_probs, t.nprob); break; }
-    case kDgrad: { auto k = gemm_kernel<kDgrad>; B200_LAUNCH(k, grid, block, 0, stream, t.d_probs, t.nprob); break; }
-    default: { auto k = gemm_kernel<kWgrad>; B200_LAUNCH(k, grid, block, 0, stream, t.d_probs, t.nprob); break; }
+    case kFwd: { auto k = gemm_kernel<kFwd>; B200_LAUNCH(k, grid, block, kGemmSmemBytes, stream, t.launch); break; }
+    case kDgrad: { auto k = gemm_kernel<kDgrad>; B200_LAUNCH(k, grid, block, kGemmSmemBytes, stream, t.launch); break; }
+    default: { auto k = gemm_kernel<kWgrad>; B200_LAUNCH(k, grid, block, kGemmSmemBytes, stream, t.launch); break; }
   }
   B200_CHECK_LAUNCH();
   return kOk;
