@@ -551,17 +551,35 @@ int b200rl_op_gemm_timed(int mode, const b200rl_gemm_problem* problems_host, int
   cudaStream_t s = as_stream(stream);
   for (int i = 0; i < warmup; ++i) B200_TRY(gemm_table_launch(t, groups, s));
 #ifndef B200_EMU
+  // the `iters` launches are captured into one CUDA graph so that the measurement sees device-side
+  // back-to-back execution (as inside the update graphs), not the host's launch rate
+  cudaStream_t cs;
+  B200_CHECK_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  B200_CHECK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+  int st = kOk;
+  for (int i = 0; i < iters && st == kOk; ++i) st = gemm_table_launch(t, groups, cs);
+  cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+  if (st != kOk) return st;
+  B200_CHECK_CUDA(ce);
+  B200_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+  B200_CHECK_CUDA(cudaGraphLaunch(exec, s));
+  B200_CHECK_CUDA(cudaStreamSynchronize(s));
   cudaEvent_t e0, e1;
   B200_CHECK_CUDA(cudaEventCreate(&e0));
   B200_CHECK_CUDA(cudaEventCreate(&e1));
   B200_CHECK_CUDA(cudaEventRecord(e0, s));
-  for (int i = 0; i < iters; ++i) B200_TRY(gemm_table_launch(t, groups, s));
+  B200_CHECK_CUDA(cudaGraphLaunch(exec, s));
   B200_CHECK_CUDA(cudaEventRecord(e1, s));
   B200_CHECK_CUDA(cudaEventSynchronize(e1));
   float ms = 0.f;
   B200_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+  cudaGraphExecDestroy(exec);
+  cudaGraphDestroy(graph);
+  cudaStreamDestroy(cs);
   *ms_per_launch = ms / (float)iters;
 #else
   for (int i = 0; i < iters; ++i) B200_TRY(gemm_table_launch(t, groups, s));

@@ -503,9 +503,11 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_cons
 // A launch table: problems are appended on the host once, then replayed (the struct is passed by value
 // as the kernel parameter; scratch / tickets for split-K live in device memory owned by the table).
 struct GemmTable {
-  GemmLaunch launch;
+  GemmLaunch launch;      // problems run by the FFMA kernel
+  GemmLaunch launch_tc;   // problems run by the tcgen05 kernel (stacked seeds; gemm_tc.cuh)
   int nprob = 0;
-  int total_tiles = 0;
+  int total_tiles = 0;    // FFMA tiles (32 x 32)
+  int tc_tiles = 0;       // tcgen05 tiles (128 rows x N)
   int mode = kFwd;
   int groups = 1;
 };

@@ -1,0 +1,390 @@
+// gemm_tc.cuh -- tcgen05 (5th-gen tensor core) grouped GEMM for STACKED seeds.
+//
+// When G independent agents are stacked (gridDim.y = seed), every layer is a real dense batch of
+// 256x256xK contractions and the FFMA path of gemm.cuh becomes compute bound (640 GFLOP per stacked
+// TD7 update).  This kernel runs the same problem table on the tensor cores:
+//   * one CTA per (problem, 128-row half, seed): D[128 x N<=256] accumulates in TMEM (256 columns),
+//   * operands stay fp32 in HBM/L2 and are consumed as TF32 (`kind::tf32`, 10-bit mantissa, fp32
+//     accumulate) -- the north star's "stated TF32 tolerance" applies to the stacked path only; the
+//     single-agent path stays fp32 FFMA,
+//   * 32-deep (128-byte) reduction chunks are staged by cp.async straight into the canonical UMMA
+//     SWIZZLE_128B shared-memory layouts (K-major for operands contiguous along the reduction,
+//     MN-major otherwise, so forward / dgrad / wgrad need no transposed copies), 2 stages x 48 KB so two
+//     CTAs share an SM and one CTA's epilogue overlaps the other's main loop,
+//   * one elected thread issues 4 x tcgen05.mma (M=128, N, K=8) per chunk and commits to an mbarrier
+//     that frees the stage; the epilogue reads TMEM with tcgen05.ld (32 lanes x 32 columns per warp)
+//     and applies the same fused epilogues as the FFMA kernel (bias+activation(+noise), act', Adam).
+// Eligibility (host): rows multiple of 128, 64 <= N <= 256 and N % 16 == 0; everything else in a table
+// (action-width layers, bias gradients) stays on the FFMA kernel in the same phase.
+#pragma once
+#ifndef B200_EMU
+#include "gemm.cuh"
+
+namespace b200rl {
+
+constexpr int kTcM = 128;
+constexpr int kTcNMax = 256;
+constexpr int kTcBK = 32;  // fp32 elements per 128-byte swizzle row
+constexpr int kTcStages = 2;
+constexpr int kTcThreads = 256;
+constexpr int kTcATileBytes = kTcM * 128;                       // 16 KB
+constexpr int kTcBTileBytes = kTcNMax * 128;                    // 32 KB
+constexpr int kTcStageBytes = kTcATileBytes + kTcBTileBytes;    // 48 KB
+constexpr int kTcSmemBytes = 1024 + kTcStages * kTcStageBytes + 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  // bounded spin: a descriptor / pipeline bug must surface as a trapped launch, never as a hung GPU
+  for (unsigned spin = 0;; ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (spin > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], TF32 inputs, fp32 accumulate, M = 128, N from the instruction descriptor
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+
+// 32 TMEM lanes x 32 consecutive 32-bit columns -> 32 registers per thread (thread t <-> lane base + t)
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B = 2 [61,64)
+// layout: 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B (the only layout the tensor core accepts
+// for MN-major 32-bit operands: 32-byte swizzle granularity, 4-row atoms)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+// 32-bit instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, fp32 accumulate
+__host__ __device__ inline uint32_t tc_instr_desc(int n, bool a_mn_major, bool b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;                        // c_format = F32
+  d |= 2u << 7;                        // a_format = TF32
+  d |= 2u << 10;                       // b_format = TF32
+  d |= (a_mn_major ? 1u : 0u) << 15;   // a_major
+  d |= (b_mn_major ? 1u : 0u) << 16;   // b_major
+  d |= (uint32_t)(n >> 3) << 17;       // n_dim
+  d |= (uint32_t)(kTcM >> 4) << 24;    // m_dim
+  return d;
+}
+
+// One operand tile (R = 128 or 256 output indices x 32 reduction indices) as seen by one thread:
+// NS = R/32 strips of 16 bytes per chunk, laid out for the UMMA SWIZZLE_128B canonical layouts:
+//   K-major  (SWIZZLE_128B)        : byte(c, r) = (c/8)*1024 + (c%8)*128 + ((r/4 ^ c%8) * 16)        (SBO = 1024)
+//   MN-major (SWIZZLE_128B_BASE32B): byte(c, r) = (c/32)*4096 + (r/4)*512 + (r%4)*128
+//                                                 + (((c%32)/8 ^ r%4) * 32) + (c%8)*4            (LBO = 4096, SBO = 512)
+template <int R, bool KMAJOR>
+struct TcOperand {
+  static constexpr int NS = R / 32;
+  const float* src[NS];
+  int dst[NS];
+  unsigned fast;   // bit t: strip t is a complete, 16-byte aligned, in-range strip (modulo the reduction bound)
+  unsigned rowok;  // bit t: K-major: output row inside the problem
+  int pos;         // K-major: 4*(tid&7); MN-major: c0 + 4*cc
+  int rr[NS];      // MN-major: reduction row of strip t inside the chunk
+  long long bump;
+
+  __device__ __forceinline__ void init(const float* base, int ld, int c0, int cmax, int tid, int r_start) {
+    fast = 0; rowok = 0;
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+      if (KMAJOR) {
+        const int c = (tid >> 3) + 32 * t, ch = tid & 7;
+        dst[t] = (c >> 3) * 1024 + (c & 7) * 128 + ((ch ^ (c & 7)) << 4);
+        pos = ch << 2;
+        rr[t] = 0;
+        const bool ok = (c0 + c) < cmax;
+        src[t] = base + (long long)(c0 + c) * ld + pos + r_start;
+        if (ok) rowok |= 1u << t;
+        if (ok && aligned16(src[t])) fast |= 1u << t;
+        bump = kTcBK;
+      } else {
+        constexpr int CPR = R / 4;  // 16-byte column chunks per reduction row
+        const int q = tid + kTcThreads * t;
+        const int r = q / CPR, cc = q % CPR;
+        const int c = cc * 4;
+        dst[t] = (c >> 5) * 4096 + (r >> 2) * 512 + (r & 3) * 128 + ((((c & 31) >> 3) ^ (r & 3)) << 5) + (((c & 7) >> 2) << 4);
+        pos = c0 + c;
+        rr[t] = r;
+        src[t] = base + (long long)(r_start + r) * ld + pos;
+        rowok |= 1u << t;
+        if (pos + 3 < cmax && aligned16(src[t])) fast |= 1u << t;
+        bump = (long long)kTcBK * ld;
+      }
+    }
+  }
+  __device__ __forceinline__ void stage(unsigned char* tile, int r0, int rlen, int cmax) {
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+      float* d = reinterpret_cast<float*>(tile + dst[t]);
+      bool in, full;
+      if (KMAJOR) { const int p = r0 + pos; in = ((rowok >> t) & 1u) && p < rlen; full = p + 3 < rlen; }
+      else { in = (r0 + rr[t]) < rlen && pos < cmax; full = true; }
+      if (((fast >> t) & 1u) && in && full) {
+        cp_async16(d, src[t]);
+      } else {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (in) {
+          const float* q = src[t];
+          const int lim = KMAJOR ? (rlen - (r0 + pos)) : (cmax - pos);
+          v.x = q[0];
+          if (lim > 1) v.y = q[1];
+          if (lim > 2) v.z = q[2];
+          if (lim > 3) v.w = q[3];
+        }
+        *reinterpret_cast<float4*>(d) = v;
+      }
+      src[t] += bump;
+    }
+  }
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kTcThreads, 2) gemm_tc_kernel(const __grid_constant__ GemmLaunch L) {
+  constexpr bool A_KM = (MODE != kWgrad);
+  constexpr bool B_KM = (MODE == kFwd);
+  extern __shared__ __align__(16) unsigned char tc_smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcStages * kTcStageBytes);  // [kTcStages] "stage free"
+  __shared__ uint32_t s_tmem_base;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = blockIdx.y;
+  const int tile_id = blockIdx.x;
+  int pi = 0;
+  while (pi + 1 < L.nprob && tile_id >= L.p[pi + 1].tile_begin) ++pi;
+  const GemmProblem& sp = L.p[pi];
+  const int i0 = (tile_id - sp.tile_begin) * kTcM;
+  const int I = sp.I, J = sp.J;
+  const int n_pad = (J + 15) & ~15;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem_base)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  if (tid == 32) {
+    for (int s = 0; s < kTcStages; ++s) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  int total_chunks = 0;
+  for (int s = 0; s < sp.nseg; ++s) total_chunks += (sp.seg[s].len + kTcBK - 1) / kTcBK;
+
+  TcOperand<kTcM, A_KM> ca;
+  TcOperand<kTcNMax, B_KM> cb;
+  int pseg = 0, pr0 = 0, plen = 0;
+  auto open_segment = [&]() {
+    const GemmSeg& sg = sp.seg[pseg];
+    plen = sg.len;
+    ca.init(sg.A + (long long)g * sg.a_gs, sg.a_ld, i0, I, tid, 0);
+    cb.init(sg.B + (long long)g * sg.b_gs, sg.b_ld, 0, J, tid, 0);
+    pr0 = 0;
+  };
+  auto issue = [&](int stage) {
+    unsigned char* At = smem + stage * kTcStageBytes;
+    unsigned char* Bt = At + kTcATileBytes;
+    ca.stage(At, pr0, plen, I);
+    cb.stage(Bt, pr0, plen, J);
+    pr0 += kTcBK;
+    if (pr0 >= plen && ++pseg < sp.nseg) open_segment();
+  };
+  open_segment();
+
+  const uint32_t idesc = tc_instr_desc(n_pad, !A_KM, !B_KM);
+  const uint32_t smem_base_u32 = smem_u32(smem);
+
+  // prologue
+#pragma unroll
+  for (int s = 0; s < kTcStages - 1; ++s) {
+    if (s < total_chunks) issue(s);
+    cp_async_commit();
+  }
+  for (int c = 0; c < total_chunks; ++c) {
+    const int s = c % kTcStages;
+    cp_async_wait<kTcStages - 2>();
+    fence_proxy_async();  // cp.async / st.shared wrote through the generic proxy; the tensor core reads through the async proxy
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a_addr = smem_base_u32 + s * kTcStageBytes;
+      const uint32_t b_addr = a_addr + kTcATileBytes;
+#pragma unroll
+      for (int kk = 0; kk < kTcBK / 8; ++kk) {
+        const uint64_t da = A_KM ? tc_smem_desc(a_addr + kk * 32, 16, 1024, 2) : tc_smem_desc(a_addr + kk * 1024, 4096, 512, 1);
+        const uint64_t db = B_KM ? tc_smem_desc(b_addr + kk * 32, 16, 1024, 2) : tc_smem_desc(b_addr + kk * 1024, 4096, 512, 1);
+        tc_mma_tf32(tmem_base, da, db, idesc, (c > 0 || kk > 0) ? 1u : 0u);
+      }
+      tc_commit(&bars[s]);  // arrives when the MMAs above (and all earlier ones) have finished reading smem / writing TMEM
+    }
+    // refill the stage consumed by chunk c-1 (= stage of chunk c + kTcStages - 1) once its MMAs are done
+    const int cn = c + kTcStages - 1;
+    if (cn < total_chunks) {
+      if (c >= 1) mbar_wait(&bars[cn % kTcStages], (uint32_t)(((c - 1) / kTcStages) & 1));
+      issue(cn % kTcStages);
+    }
+    cp_async_commit();
+  }
+  cp_async_wait<0>();
+  if (total_chunks > 0) {
+    const int last = total_chunks - 1;
+    mbar_wait(&bars[last % kTcStages], (uint32_t)((last / kTcStages) & 1));
+  }
+  tc_fence_after();
+
+  // ---- epilogue: warp w reads TMEM lanes [32*(w&3), +32) (its rows) and columns [128*(w>>2), +128) ----
+  const int row = i0 + 32 * (warp & 3) + lane;
+  const int colhalf = (warp >> 2) * 128;
+  const bool row_ok = row < I;
+#pragma unroll 1
+  for (int cc = 0; cc < 4; ++cc) {
+    const int col0 = colhalf + cc * 32;
+    if (col0 >= n_pad) break;  // uniform across the warp
+    float v[32];
+    if (total_chunks > 0) {
+      tc_ld32(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0, v);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = 0.f;
+    }
+    if (!row_ok) continue;
+    const int nvalid = min(32, J - col0);
+    if (nvalid <= 0) continue;
+    if (MODE == kFwd) {
+      const float* bias = sp.bias ? sp.bias + (long long)g * sp.bias_gs + col0 : nullptr;
+      const float* noise = (sp.act == kActTanhNoise) ? sp.aux + (long long)g * sp.aux_gs + (long long)row * sp.aux_ld + col0 : nullptr;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        if (e < nvalid) {
+          float x = v[e] + (bias ? bias[e] : 0.f);
+          x = act_forward(x, sp.act);
+          if (noise) {
+            const float n = fminf(fmaxf(noise[e] * sp.noise_sigma, -sp.noise_clip), sp.noise_clip);
+            x = fminf(fmaxf(x + n, -1.f), 1.f);
+          }
+          v[e] = x;
+        }
+      }
+    } else if (MODE == kDgrad) {
+      const float* Cold = sp.C + (long long)g * sp.c_gs + (long long)row * sp.c_ld + col0;
+      const float* H = sp.aux ? sp.aux + (long long)g * sp.aux_gs + (long long)row * sp.aux_ld + col0 : nullptr;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        if (e < nvalid) {
+          float x = v[e];
+          if (sp.accumulate) x += Cold[e];
+          if (H) x *= act_backward(H[e], sp.act);
+          v[e] = x;
+        }
+      }
+    } else {
+      if (sp.P) {
+        const AdamScalars sc = *sp.adam;
+        const long long off = (long long)g * sp.p_gs + (long long)row * sp.p_ld + col0;
+        float* Pp = sp.P + off;
+        float* Mp = sp.M + off;
+        float* Vp = sp.V + off;
+        if (nvalid == 32 && aligned16(Pp)) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            float4 p4 = *reinterpret_cast<float4*>(Pp + e), m4 = *reinterpret_cast<float4*>(Mp + e), v4 = *reinterpret_cast<float4*>(Vp + e);
+            adam_update(v[e + 0], p4.x, m4.x, v4.x, sc);
+            adam_update(v[e + 1], p4.y, m4.y, v4.y, sc);
+            adam_update(v[e + 2], p4.z, m4.z, v4.z, sc);
+            adam_update(v[e + 3], p4.w, m4.w, v4.w, sc);
+            *reinterpret_cast<float4*>(Pp + e) = p4;
+            *reinterpret_cast<float4*>(Mp + e) = m4;
+            *reinterpret_cast<float4*>(Vp + e) = v4;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            if (e < nvalid) {
+              float p = Pp[e], m = Mp[e], vv = Vp[e];
+              adam_update(v[e], p, m, vv, sc);
+              Pp[e] = p; Mp[e] = m; Vp[e] = vv;
+            }
+          }
+        }
+      }
+      if (!sp.C) continue;
+    }
+    float* Crow = sp.C + (long long)g * sp.c_gs + (long long)row * sp.c_ld + col0;
+    if (nvalid == 32 && aligned16(Crow)) {
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(Crow + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        if (e < nvalid) Crow[e] = v[e];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+inline bool tc_eligible(const GemmProblem& p) {
+  if (p.I % kTcM != 0 || p.J < 64 || p.J > kTcNMax || (p.J % 16) != 0) return false;
+  for (int s = 0; s < p.nseg; ++s)
+    if (p.seg[s].b_ones) return false;
+  return true;
+}
+
+}  // namespace b200rl
+#endif  // !B200_EMU

@@ -1,10 +1,12 @@
 // host.cuh -- host-side plumbing: error string, device buffers, launch tables, launchers.
 #pragma once
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
 #include "common.cuh"
 #include "gemm.cuh"
+#include "gemm_tc.cuh"
 #include "ops.cuh"
 
 namespace b200rl {
@@ -60,8 +62,10 @@ inline void add_seg(GemmProblem& p, const float* A, int a_ld, long long a_gs, co
   s.b_ones = 0;
 }
 
-// choose how many CTAs share one output tile: enough to put ~3 CTAs on each of the 148 SMs, never more
-// than the longest problem has reduction chunks, never when stacked seeds already fill the machine
+// How many CTAs share one output tile.  Measured on B200 (profiles/sweep_gemm.py, graph-timed): a launch
+// costs ~4 us fixed + ~0.76 us per 64-deep chunk per CTA, and the ticket/scratch round trip of a split
+// costs ~1.5-2 us, so splitting only pays for long reductions (K >= 512) of launches that leave most SMs
+// idle (<= 64 tiles); everything else runs unsplit.
 inline int choose_splitk(const std::vector<GemmProblem>& probs, int tiles, int groups) {
   int max_chunks = 1;
   for (const auto& p : probs) {
@@ -69,31 +73,64 @@ inline int choose_splitk(const std::vector<GemmProblem>& probs, int tiles, int g
     for (int s = 0; s < p.nseg; ++s) c += ceil_div(p.seg[s].len, kBK);
     max_chunks = std::max(max_chunks, c);
   }
-  const long long ctas = (long long)tiles * groups;
-  int s = (int)(444 / std::max<long long>(ctas, 1));
-  s = std::max(1, std::min(s, std::min(max_chunks, 8)));
-  return s;
+  if ((long long)tiles * groups <= 64 && max_chunks >= 8) return 2;
+  return 1;
+}
+
+// Stacked seeds (groups >= kTcMinGroups) run their eligible problems on the tensor cores (TF32);
+// B200RL_TC=0/1 overrides (tests, A/B measurements).
+constexpr int kTcMinGroups = 8;
+inline bool use_tensor_cores(int groups) {
+#ifdef B200_EMU
+  (void)groups;
+  return false;
+#else
+  if (const char* e = getenv("B200RL_TC")) return atoi(e) != 0;
+  return groups >= kTcMinGroups;
+#endif
 }
 
 inline int gemm_table_upload(GemmTable* t, int mode, std::vector<GemmProblem>& probs, DeviceArena* arena, int groups = 1, int force_splitk = 0) {
   B200_REQUIRE((int)probs.size() <= kMaxProblems, "too many problems in one gemm launch");
-  int tiles = 0;
+  std::vector<GemmProblem> ff, tc;
+  const bool want_tc = use_tensor_cores(groups);
   for (auto& p : probs) {
     B200_REQUIRE(p.nseg >= 1 && p.nseg <= 3, "gemm problem needs 1..3 segments");
     B200_REQUIRE(p.I > 0 && p.J > 0, "gemm problem with empty output");
+#ifndef B200_EMU
+    if (want_tc && tc_eligible(p)) { tc.push_back(p); continue; }
+#endif
+    ff.push_back(p);
+  }
+  (void)want_tc;
+  int tiles = 0;
+  for (auto& p : ff) {
     p.tile_begin = tiles;
     p.tiles_j = ceil_div(p.J, kTile);
     tiles += ceil_div(p.I, kTile) * p.tiles_j;
   }
+  int tct = 0;
+  for (auto& p : tc) {
+    p.tile_begin = tct;
+    p.tiles_j = 1;
+    tct += p.I / 128;
+  }
   t->mode = mode;
   t->nprob = (int)probs.size();
   t->total_tiles = tiles;
+  t->tc_tiles = tct;
   t->groups = groups;
   memset(&t->launch, 0, sizeof(t->launch));
-  for (size_t i = 0; i < probs.size(); ++i) t->launch.p[i] = probs[i];
-  t->launch.nprob = t->nprob;
+  memset(&t->launch_tc, 0, sizeof(t->launch_tc));
+  for (size_t i = 0; i < ff.size(); ++i) t->launch.p[i] = ff[i];
+  for (size_t i = 0; i < tc.size(); ++i) t->launch_tc.p[i] = tc[i];
+  t->launch.nprob = (int)ff.size();
   t->launch.total_tiles = tiles;
-  t->launch.splitk = force_splitk > 0 ? force_splitk : choose_splitk(probs, tiles, groups);
+  t->launch_tc.nprob = (int)tc.size();
+  t->launch_tc.total_tiles = tct;
+  t->launch_tc.splitk = 1;
+  if (const char* e = getenv("B200RL_SPLITK")) force_splitk = atoi(e);  // tuning knob (profiles/sweep_gemm.py)
+  t->launch.splitk = ff.empty() ? 1 : (force_splitk > 0 ? force_splitk : choose_splitk(ff, tiles, groups));
   if (t->launch.splitk > 1) {
     B200_TRY(arena->alloc(&t->launch.scratch, (size_t)groups * tiles * t->launch.splitk * kTileElems));
     B200_TRY(arena->alloc(&t->launch.tickets, (size_t)groups * tiles));
@@ -107,22 +144,36 @@ inline int gemm_table_launch(const GemmTable& t, int groups, cudaStream_t stream
     set_last_error("gemm table launched with a different number of groups than it was built for");
     return kErrState;
   }
-  dim3 grid((unsigned)(t.total_tiles * t.launch.splitk), (unsigned)groups, 1), block(kGemmThreads, 1, 1);
 #ifndef B200_EMU
-  static bool attr_set = false;  // 48 KB of dynamic shared memory needs the opt-in once per kernel
+  static bool attr_set = false;  // > 48 KB of dynamic shared memory needs the opt-in once per kernel
   if (!attr_set) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<kFwd>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
     B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<kDgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
     B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<kWgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kFwd>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kDgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kWgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
     attr_set = true;
   }
-#endif
-  switch (t.mode) {
-    case kFwd: { auto k = gemm_kernel<kFwd>; B200_LAUNCH(k, grid, block, kGemmSmemBytes, stream, t.launch); break; }
-    case kDgrad: { auto k = gemm_kernel<kDgrad>; B200_LAUNCH(k, grid, block, kGemmSmemBytes, stream, t.launch); break; }
-    default: { auto k = gemm_kernel<kWgrad>; B200_LAUNCH(k, grid, block, kGemmSmemBytes, stream, t.launch); break; }
+  if (t.launch_tc.nprob > 0) {
+    dim3 grid((unsigned)t.tc_tiles, (unsigned)groups, 1), block(kTcThreads, 1, 1);
+    switch (t.mode) {
+      case kFwd: { auto k = gemm_tc_kernel<kFwd>; B200_LAUNCH(k, grid, block, kTcSmemBytes, stream, t.launch_tc); break; }
+      case kDgrad: { auto k = gemm_tc_kernel<kDgrad>; B200_LAUNCH(k, grid, block, kTcSmemBytes, stream, t.launch_tc); break; }
+      default: { auto k = gemm_tc_kernel<kWgrad>; B200_LAUNCH(k, grid, block, kTcSmemBytes, stream, t.launch_tc); break; }
+    }
+    B200_CHECK_LAUNCH();
   }
-  B200_CHECK_LAUNCH();
+#endif
+  if (t.launch.nprob > 0) {
+    dim3 grid((unsigned)(t.total_tiles * t.launch.splitk), (unsigned)groups, 1), block(kGemmThreads, 1, 1);
+    switch (t.mode) {
+      case kFwd: { auto k = gemm_kernel<kFwd>; B200_LAUNCH(k, grid, block, kGemmSmemBytes, stream, t.launch); break; }
+      case kDgrad: { auto k = gemm_kernel<kDgrad>; B200_LAUNCH(k, grid, block, kGemmSmemBytes, stream, t.launch); break; }
+      default: { auto k = gemm_kernel<kWgrad>; B200_LAUNCH(k, grid, block, kGemmSmemBytes, stream, t.launch); break; }
+    }
+    B200_CHECK_LAUNCH();
+  }
   return kOk;
 }
 

@@ -240,3 +240,58 @@ def test_free_running_drift_is_bounded(dev, name):
     print(f"{name}: free-running weight drift after {steps} updates = {worst:.2e} (normwise)")
     dev.check(dev.lib.b200rl_agent_destroy(h))
     dev.check(dev.lib.b200rl_replay_destroy(r))
+
+
+def test_stacked_seeds_equal_independent_agents(dev, monkeypatch):
+    """n_seeds = 2 stacked in one engine (gridDim.y = seed) must reproduce, bit for bit, two
+    independent single-seed engines fed the same per-seed weights, batches, uniforms and noise.
+    (Split-K is pinned to 1: the split factor is chosen from the CTA count, which differs between
+    1 and 2 seeds, and changes the fp32 summation order in the last bit.)"""
+    monkeypatch.setenv("B200RL_SPLITK", "1")
+    from oracle import agents as oagents
+    from oracle import replay as oreplay
+
+    torch.set_num_threads(1)
+    env, G, steps, rows_n = "Hopper-v4", 2, 4, 2048
+    S, A = 11, 3
+    kwargs = dict(use_lap=True, target_update_rate=3)
+    oracles = []
+    for g in range(G):
+        torch.manual_seed(100 + g)
+        oracles.append(oagents.OracleTD7(env, **kwargs))
+    stacked = make_c_agent(dev, "TD7", oracles[0], kwargs, keep_grads=0, groups=G)
+    singles = [make_c_agent(dev, "TD7", oracles[g], kwargs, keep_grads=0) for g in range(G)]
+    rs = dev.replay_create(rows_n, S, A, groups=G)
+    rsingle = [dev.replay_create(rows_n, S, A) for _ in range(G)]
+    for g in range(G):
+        push_state(dev, stacked, "TD7", oracles[g], group=g)
+        push_state(dev, singles[g], "TD7", oracles[g])
+        rows = oreplay.synthetic_rows(rows_n, S, A, seed=50 + g)
+        packed = dev.pack_rows(rs, rows["state"], rows["action"], rows["reward"], rows["next_state"], rows["done"])
+        dev.replay_append(rs, packed, group=g)
+        dev.replay_append(rsingle[g], packed)
+    rng = np.random.default_rng(0)
+    for t in range(steps):
+        u = rng.random((G, gu.BATCH), dtype=np.float32)
+        nz = rng.standard_normal((G, gu.BATCH, A)).astype(np.float32)
+        idx, batch, ptrs = dev.replay_sample(rs, gu.BATCH, S, A, u=u, groups=G)
+        for g in range(G):
+            off = lambda key, d: ptrs[key] + 4 * g * gu.BATCH * d  # noqa: E731
+            dev.check(dev.lib.b200rl_agent_stage_batch(stacked, g, off("state", S), off("action", A), off("reward", 1), off("next_state", S), off("done", 1), None))
+        dev.check(dev.lib.b200rl_agent_update(stacked, rs, dev.to_dev(nz), None))
+        dev.check(dev.lib.b200rl_stream_sync(None))
+        for g in range(G):
+            i1, b1, p1 = dev.replay_sample(rsingle[g], gu.BATCH, S, A, u=u[g])
+            assert np.array_equal(i1[0], idx[g])
+            dev.check(dev.lib.b200rl_agent_stage_batch(singles[g], 0, p1["state"], p1["action"], p1["reward"], p1["next_state"], p1["done"], None))
+            dev.check(dev.lib.b200rl_agent_update(singles[g], rsingle[g], dev.to_dev(nz[g]), None))
+            dev.check(dev.lib.b200rl_stream_sync(None))
+            assert np.array_equal(dev.read_info(stacked, t + 1, group=g), dev.read_info(singles[g], t + 1)), (t, g)
+    for g in range(G):
+        for nid in range(8):
+            for (w1, b1), (w2, b2) in zip(dev.read_net(stacked, nid, group=g), dev.read_net(singles[g], nid)):
+                assert np.array_equal(w1, w2) and np.array_equal(b1, b2), (g, nid)
+        assert np.array_equal(dev.replay_priority(rs, rows_n, group=g), dev.replay_priority(rsingle[g], rows_n))
+        assert dev.replay_state(rs, g)[2] == dev.replay_state(rsingle[g])[2]
+    # seeds really are different agents
+    assert not np.array_equal(dev.read_net(stacked, 1, group=0)[1][0], dev.read_net(stacked, 1, group=1)[1][0])
