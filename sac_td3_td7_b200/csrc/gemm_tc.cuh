@@ -285,92 +285,77 @@ __global__ void __launch_bounds__(kTcThreads, 2) gemm_tc_kernel(const __grid_con
   }
   tc_fence_after();
 
-  // ---- epilogue: warp w reads TMEM lanes [32*(w&3), +32) (its rows) and columns [128*(w>>2), +128) ----
-  const int row = i0 + 32 * (warp & 3) + lane;
+  // ---- epilogue ----
+  // warp w owns TMEM lanes [32*(w&3), +32) (its 32 output rows) and columns [128*(w>>2), +128).  tcgen05.ld
+  // hands every thread one ROW (32 consecutive columns); going to global memory like that would make each
+  // warp instruction touch 32 different rows.  So each 32x32 block is transposed through a padded
+  // shared-memory tile (the pipeline stages are free now) and written row by row with lane = column:
+  // every global access of the epilogue -- C, bias, aux, and Adam's p/m/v -- is a coalesced 128-byte line.
+  float* st = reinterpret_cast<float*>(smem) + warp * (32 * 33);
+  const int row_base = i0 + 32 * (warp & 3);
   const int colhalf = (warp >> 2) * 128;
-  const bool row_ok = row < I;
 #pragma unroll 1
   for (int cc = 0; cc < 4; ++cc) {
     const int col0 = colhalf + cc * 32;
     if (col0 >= n_pad) break;  // uniform across the warp
-    float v[32];
-    if (total_chunks > 0) {
-      tc_ld32(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0, v);
-    } else {
+    {
+      float v[32];
+      if (total_chunks > 0) {
+        tc_ld32(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0, v);
+      } else {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) v[e] = 0.f;
+        for (int e = 0; e < 32; ++e) v[e] = 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 32; ++e) st[lane * 33 + e] = v[e];
     }
-    if (!row_ok) continue;
-    const int nvalid = min(32, J - col0);
-    if (nvalid <= 0) continue;
+    __syncwarp();
+    const int col = col0 + lane;
+    const bool col_ok = col < J;
+    const int nrows = min(32, I - row_base);
     if (MODE == kFwd) {
-      const float* bias = sp.bias ? sp.bias + (long long)g * sp.bias_gs + col0 : nullptr;
-      const float* noise = (sp.act == kActTanhNoise) ? sp.aux + (long long)g * sp.aux_gs + (long long)row * sp.aux_ld + col0 : nullptr;
-#pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        if (e < nvalid) {
-          float x = v[e] + (bias ? bias[e] : 0.f);
-          x = act_forward(x, sp.act);
-          if (noise) {
-            const float n = fminf(fmaxf(noise[e] * sp.noise_sigma, -sp.noise_clip), sp.noise_clip);
-            x = fminf(fmaxf(x + n, -1.f), 1.f);
-          }
-          v[e] = x;
+      const float bias = (sp.bias && col_ok) ? sp.bias[(long long)g * sp.bias_gs + col] : 0.f;
+      const bool has_noise = (sp.act == kActTanhNoise);
+      for (int rr = 0; rr < nrows; ++rr) {
+        if (!col_ok) continue;
+        const int row = row_base + rr;
+        float x = act_forward(st[rr * 33 + lane] + bias, sp.act);
+        if (has_noise) {
+          const float nz = sp.aux[(long long)g * sp.aux_gs + (long long)row * sp.aux_ld + col];
+          const float n = fminf(fmaxf(nz * sp.noise_sigma, -sp.noise_clip), sp.noise_clip);
+          x = fminf(fmaxf(x + n, -1.f), 1.f);
         }
+        sp.C[(long long)g * sp.c_gs + (long long)row * sp.c_ld + col] = x;
       }
     } else if (MODE == kDgrad) {
-      const float* Cold = sp.C + (long long)g * sp.c_gs + (long long)row * sp.c_ld + col0;
-      const float* H = sp.aux ? sp.aux + (long long)g * sp.aux_gs + (long long)row * sp.aux_ld + col0 : nullptr;
-#pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        if (e < nvalid) {
-          float x = v[e];
-          if (sp.accumulate) x += Cold[e];
-          if (H) x *= act_backward(H[e], sp.act);
-          v[e] = x;
-        }
+      for (int rr = 0; rr < nrows; ++rr) {
+        if (!col_ok) continue;
+        const int row = row_base + rr;
+        float* cptr = sp.C + (long long)g * sp.c_gs + (long long)row * sp.c_ld + col;
+        float x = st[rr * 33 + lane];
+        if (sp.accumulate) x += *cptr;
+        if (sp.aux) x *= act_backward(sp.aux[(long long)g * sp.aux_gs + (long long)row * sp.aux_ld + col], sp.act);
+        *cptr = x;
       }
     } else {
-      if (sp.P) {
-        const AdamScalars sc = *sp.adam;
-        const long long off = (long long)g * sp.p_gs + (long long)row * sp.p_ld + col0;
-        float* Pp = sp.P + off;
-        float* Mp = sp.M + off;
-        float* Vp = sp.V + off;
-        if (nvalid == 32 && aligned16(Pp)) {
-#pragma unroll
-          for (int e = 0; e < 32; e += 4) {
-            float4 p4 = *reinterpret_cast<float4*>(Pp + e), m4 = *reinterpret_cast<float4*>(Mp + e), v4 = *reinterpret_cast<float4*>(Vp + e);
-            adam_update(v[e + 0], p4.x, m4.x, v4.x, sc);
-            adam_update(v[e + 1], p4.y, m4.y, v4.y, sc);
-            adam_update(v[e + 2], p4.z, m4.z, v4.z, sc);
-            adam_update(v[e + 3], p4.w, m4.w, v4.w, sc);
-            *reinterpret_cast<float4*>(Pp + e) = p4;
-            *reinterpret_cast<float4*>(Mp + e) = m4;
-            *reinterpret_cast<float4*>(Vp + e) = v4;
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            if (e < nvalid) {
-              float p = Pp[e], m = Mp[e], vv = Vp[e];
-              adam_update(v[e], p, m, vv, sc);
-              Pp[e] = p; Mp[e] = m; Vp[e] = vv;
-            }
-          }
+      AdamScalars sc;
+      if (sp.P) sc = *sp.adam;
+      for (int rr = 0; rr < nrows; ++rr) {
+        if (!col_ok) continue;
+        const int row = row_base + rr;
+        const float gval = st[rr * 33 + lane];
+        if (sp.P) {
+          const long long off = (long long)g * sp.p_gs + (long long)row * sp.p_ld + col;
+          float pv = sp.P[off], mv = sp.M[off], vv = sp.V[off];
+          adam_update(gval, pv, mv, vv, sc);
+          sp.P[off] = pv;
+          sp.M[off] = mv;
+          sp.V[off] = vv;
         }
+        if (sp.C) sp.C[(long long)g * sp.c_gs + (long long)row * sp.c_ld + col] = gval;
       }
-      if (!sp.C) continue;
     }
-    float* Crow = sp.C + (long long)g * sp.c_gs + (long long)row * sp.c_ld + col0;
-    if (nvalid == 32 && aligned16(Crow)) {
-#pragma unroll
-      for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(Crow + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-    } else {
-#pragma unroll
-      for (int e = 0; e < 32; ++e)
-        if (e < nvalid) Crow[e] = v[e];
-    }
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();

@@ -27,6 +27,9 @@ namespace b200rl {
 
 constexpr int kPrioTile = 256;       // priorities per tile (one warp: 32 lanes x 8)
 constexpr int kPrioTilesPerCta = 8;  // 2048 priorities per CTA in the reduce kernel
+// draws handled by one warp of the search/gather kernel: 1 for a single agent (latency), 4 when many seeds
+// are stacked (fewer CTAs re-scan the tile sums)
+inline int samples_per_warp(int groups) { return groups >= 8 ? 4 : 1; }
 
 __global__ void __launch_bounds__(256) lap_tile_sums_kernel(const float* __restrict__ priority, long long prio_gs, int size,
                                                             double* __restrict__ tile_sums, int ntiles, long long ts_gs) {
@@ -69,6 +72,7 @@ struct SampleArgs {
   float* done; long long done_gs;
   int B;
   int prioritized;
+  int spw;  // samples per warp
 };
 
 __global__ void __launch_bounds__(256) lap_sample_kernel(SampleArgs a) {
@@ -98,7 +102,9 @@ __global__ void __launch_bounds__(256) lap_sample_kernel(SampleArgs a) {
     __syncthreads();
   }
 
-  const int b = blockIdx.x * 8 + warp;
+  // each warp takes kSamplesPerWarp draws in turn (fewer CTAs re-scan the tile sums)
+  for (int sw = 0; sw < a.spw; ++sw) {
+  const int b = (blockIdx.x * 8 + warp) * a.spw + sw;
   if (b >= a.B) return;
 
   float u;
@@ -184,6 +190,7 @@ __global__ void __launch_bounds__(256) lap_sample_kernel(SampleArgs a) {
       else if (pos < o_end) ns[pos - o_next] = val;
     }
   }
+  }  // samples of this warp
 }
 
 __global__ void __launch_bounds__(1024) lap_update_priority_kernel(float* __restrict__ priority, long long prio_gs, float* __restrict__ max_priority,
@@ -328,7 +335,8 @@ struct Replay {
     a.done = o.done; a.done_gs = o.done_gs;
     a.B = B;
     a.prioritized = prioritized ? 1 : 0;
-    dim3 grid((unsigned)ceil_div(B, 8), (unsigned)groups), block(256);
+    a.spw = samples_per_warp(groups);
+    dim3 grid((unsigned)ceil_div(B, 8 * a.spw), (unsigned)groups), block(256);
     const size_t smem = prioritized ? (size_t)ntiles * sizeof(double) : 0;
     B200_LAUNCH(lap_sample_kernel, grid, block, smem, stream, a);
     B200_CHECK_LAUNCH();

@@ -148,6 +148,24 @@ class Agent(ABC):
         self._pull()
         return self._mods[attr]
 
+    def read_infos(self, first_step: int, count: int, seed: int = 0) -> np.ndarray:
+        """[count, len(INFO_KEYS)] info rows of stacked seed `seed` for updates first_step.. (1-based)."""
+        buf = np.empty((count, len(self.INFO_KEYS)), np.float32)
+        _lib.check(self._lib.b200rl_agent_read_info(self._h, first_step, count, seed, buf.ctypes.data, _stream()))
+        return buf
+
+    def seed_population(self, base_seed: int) -> None:
+        """Give every stacked seed its own initial networks: seed g is built exactly like a fresh
+        single agent under ``torch.manual_seed(base_seed + g)`` (the reference runs seeds as separate
+        processes, scripts/td7_exp.sh:1-4)."""
+        for g in range(self.n_seeds):
+            torch.manual_seed(base_seed + g)
+            self.set_seed_weights(g, self._fresh_modules())
+        self._dirty_dev, self._dirty_host = True, False
+
+    def _fresh_modules(self) -> dict:
+        raise NotImplementedError
+
     def set_seed_weights(self, seed: int, modules: dict):
         """Load the networks of stacked seed `seed` from a dict attr -> module (population setup)."""
         for nid, (attr, names) in enumerate(self.NETS):

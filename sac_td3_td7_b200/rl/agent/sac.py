@@ -55,6 +55,10 @@ class SAC(_MlpAgent):
         """sac.py:80-86"""
         return MLPActor(state_dim, action_dim * 2), MLPCritic(state_dim, action_dim), MLPCritic(state_dim, action_dim)
 
+    def _fresh_modules(self) -> dict:
+        policy, q1, q2 = self.make_nn(self.state_dim, self.action_dim)
+        return dict(policy=policy, q1=q1, q2=q2, target_q1=q1, target_q2=q2)
+
     @property
     def tmp(self):
         """log-temperature parameter in auto mode (sac.py:55-60), else the fixed temperature."""

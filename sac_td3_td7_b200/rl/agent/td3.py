@@ -89,6 +89,10 @@ class TD3(_MlpAgent):
 
     target_policy = property(lambda self: self._module("policy"))  # aliased (td3.py:86)
 
+    def _fresh_modules(self) -> dict:
+        policy, q1, q2 = self.make_nn(self.state_dim, self.action_dim)
+        return dict(policy=policy, q1=q1, q2=q2, target_q1=q1, target_q2=q2)
+
     def make_nn(self, state_dim: int, action_dim: int):
         """td3.py:76-81"""
         return MLPActor(state_dim, action_dim), MLPCritic(state_dim, action_dim), MLPCritic(state_dim, action_dim)

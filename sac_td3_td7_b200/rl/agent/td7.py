@@ -69,6 +69,10 @@ class TD7(Agent):
         q2 = SALECritic(state_dim, action_dim, zs_dim, hdim)
         return policy, q1, q2, encoder
 
+    def _fresh_modules(self) -> dict:
+        policy, q1, q2, encoder = self.make_nn(self.state_dim, self.action_dim, self.zs_dim, self.hdim)
+        return dict(encoder=encoder, policy=policy, q1=q1, q2=q2, target_q1=q1, target_q2=q2, fixed_encoder=encoder, fixed_encoder_target=encoder)
+
     def _create_engine(self):
         cfg = _lib.TD7Config(state_dim=self.state_dim, action_dim=self.action_dim, hdim=self.hdim, zs_dim=self.zs_dim, batch=self.batch_size,
                              groups=self.n_seeds, discount=self.discount_factor, policy_lr=self.policy_lr, critic_lr=self.critic_lr,

@@ -149,3 +149,32 @@ def test_no_cpu_fallback_paths():
 
     with pytest.raises(_lib.B200RLError):
         bnn.AvgL1Norm(torch.randn(4, 8))  # CPU tensor: refused, not silently computed on the host
+
+
+def test_stacked_population_on_tensor_cores():
+    """8 stacked seeds -> the tcgen05 (TF32) path.  Seed 0 shares weights, transitions and Philox
+    streams with a single fp32 (FFMA) agent, so its losses must track that agent within the TF32
+    tolerance; the other seeds must be distinct, finite learners."""
+    from sac_td3_td7_b200.rl.agent import TD7
+    from sac_td3_td7_b200.rl.replay_memory import LAPReplayMemory
+
+    env, G, steps = "Ant-v4", 8, 8
+    pop = TD7(env, use_lap=True, n_seeds=G)
+    pop.seed_population(500)
+    buf = LAPReplayMemory(8192, env, n_seeds=G, share_rows=True)
+    buf.fill_synthetic(8192, seed=3)
+    torch.manual_seed(500)
+    one = TD7(env, use_lap=True)
+    b1 = LAPReplayMemory(8192, env)
+    b1.fill_synthetic(8192, seed=3)
+    pop.train_ops_n(steps, buf)
+    one.train_ops_n(steps, b1)
+    ref = one.read_infos(1, steps)
+    got0 = pop.read_infos(1, steps, seed=0)
+    assert np.all(np.isfinite(got0))
+    # encoder / critic losses (columns 0, 1) every step; policy loss (column 2) on even steps only
+    assert np.abs(got0[:, :2] - ref[:, :2]).max() <= 2e-2 * np.abs(ref[:, :2]).max(), (got0, ref)
+    assert np.abs(got0[1::2, 2] - ref[1::2, 2]).max() <= 5e-2 * max(np.abs(ref[1::2, 2]).max(), 0.05), (got0, ref)
+    others = [pop.read_infos(1, steps, seed=g) for g in range(1, G)]
+    for o in others:
+        assert np.all(np.isfinite(o[:, :2])) and not np.allclose(o[:, :2], got0[:, :2])
