@@ -62,6 +62,7 @@ struct AgentBase {
   int info_cols = 0;
   long long n_calls = 0;  // host mirror of StepState.n_runs
   unsigned long long rng_seed = 0xB200B200ULL;
+  unsigned low_priority_streams = 0;  // bit i: fork.side[i] carries slack work (set by the subclass before init_common)
 
   // activation arena (two-pass layout)
   float* act_base = nullptr;
@@ -97,8 +98,12 @@ struct AgentBase {
   int init_common(int nopt_, int info_cols_, const OptimHyper* hyper) {
     nopt = nopt_;
     info_cols = info_cols_;
-    B200_CHECK_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    B200_TRY(fork.init(stream, 4, 64));
+    {
+      int least = 0, greatest = 0;
+      B200_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      B200_CHECK_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, greatest));
+    }
+    B200_TRY(fork.init(stream, 4, 64, low_priority_streams));
     B200_TRY(arena.alloc(&d_step, 1));
     B200_TRY(arena.alloc(&d_adam, (size_t)nopt));
     B200_TRY(arena.alloc(&d_hyper, (size_t)nopt));

@@ -79,6 +79,7 @@ struct TD7Agent : AgentBase {
     B200_REQUIRE(B > 0 && B <= 1024, "td7: batch size must be in 1..1024");
     B200_REQUIRE(H <= 1024 && Z <= 1024, "td7: hidden sizes above 1024 are not supported");
     OptimHyper hy[3] = {{c.policy_lr, 0.9, 0.999, 1e-8}, {c.critic_lr, 0.9, 0.999, 1e-8}, {c.policy_lr, 0.9, 0.999, 1e-8}};  // policy, q, encoder
+    low_priority_streams = 0x3u;  // side[0] = encoder branch, side[1] = hoisted actor forward
     B200_TRY(init_common(3, 3, hy));
     B200_TRY(alloc_net(&enc, make_layout(kNetSaleEncoder, S, A, H, Z), true, d_adam + 2));
     B200_TRY(alloc_net(&pol, make_layout(kNetSaleActor, S, A, H, Z), true, d_adam + 0));

@@ -19,6 +19,9 @@
 #pragma once
 #ifndef B200_EMU
 #include "gemm.cuh"
+#ifndef B200RL_TC_SPIN_ALL
+#define B200RL_TC_SPIN_ALL 1
+#endif
 
 namespace b200rl {
 
@@ -255,9 +258,10 @@ __global__ void __launch_bounds__(kTcThreads, 2) gemm_tc_kernel(const __grid_con
   }
   for (int c = 0; c < total_chunks; ++c) {
     const int s = c % kTcStages;
+    const int cn = c + kTcStages - 1;  // chunk to prefetch: reuses the stage read by the MMAs of chunk c-1
     cp_async_wait<kTcStages - 2>();
     fence_proxy_async();  // cp.async / st.shared wrote through the generic proxy; the tensor core reads through the async proxy
-    __syncthreads();
+    __syncthreads();      // chunk c has landed for everybody
     if (tid == 0) {
       tc_fence_after();
       const uint32_t a_addr = smem_base_u32 + s * kTcStageBytes;
@@ -269,20 +273,27 @@ __global__ void __launch_bounds__(kTcThreads, 2) gemm_tc_kernel(const __grid_con
         tc_mma_tf32(tmem_base, da, db, idesc, (c > 0 || kk > 0) ? 1u : 0u);
       }
       tc_commit(&bars[s]);  // arrives when the MMAs above (and all earlier ones) have finished reading smem / writing TMEM
+      // the MMAs of chunk c are queued behind those of chunk c-1; wait (one thread only -- a block of spinning
+      // threads would eat the issue slots) until chunk c-1 is done so that its stage can be refilled
     }
-    // refill the stage consumed by chunk c-1 (= stage of chunk c + kTcStages - 1) once its MMAs are done
-    const int cn = c + kTcStages - 1;
-    if (cn < total_chunks) {
-      if (c >= 1) mbar_wait(&bars[cn % kTcStages], (uint32_t)(((c - 1) / kTcStages) & 1));
-      issue(cn % kTcStages);
+#if B200RL_TC_SPIN_ALL
+    if (c >= 1 && cn < total_chunks) mbar_wait(&bars[cn % kTcStages], (uint32_t)(((c - 1) / kTcStages) & 1));
+#else
+    if (c >= 1 && cn < total_chunks) {
+      if (tid == 0) mbar_wait(&bars[cn % kTcStages], (uint32_t)(((c - 1) / kTcStages) & 1));
+      __syncthreads();  // uniform condition: publish "stage cn%S is free"
     }
+#endif
+    if (cn < total_chunks) issue(cn % kTcStages);
     cp_async_commit();
   }
   cp_async_wait<0>();
-  if (total_chunks > 0) {
+  if (total_chunks > 0 && tid == 0) {
     const int last = total_chunks - 1;
     mbar_wait(&bars[last % kTcStages], (uint32_t)((last / kTcStages) & 1));
   }
+  tc_fence_before();
+  __syncthreads();
   tc_fence_after();
 
   // ---- epilogue ----
@@ -313,46 +324,69 @@ __global__ void __launch_bounds__(kTcThreads, 2) gemm_tc_kernel(const __grid_con
     const int col = col0 + lane;
     const bool col_ok = col < J;
     const int nrows = min(32, I - row_base);
+    constexpr int U = 8;  // rows in flight: all global loads of a batch are issued before the first use
     if (MODE == kFwd) {
+      // (the smoothing-noise epilogue never reaches this kernel: its layer has J = action_dim < 64)
       const float bias = (sp.bias && col_ok) ? sp.bias[(long long)g * sp.bias_gs + col] : 0.f;
-      const bool has_noise = (sp.act == kActTanhNoise);
-      for (int rr = 0; rr < nrows; ++rr) {
-        if (!col_ok) continue;
-        const int row = row_base + rr;
-        float x = act_forward(st[rr * 33 + lane] + bias, sp.act);
-        if (has_noise) {
-          const float nz = sp.aux[(long long)g * sp.aux_gs + (long long)row * sp.aux_ld + col];
-          const float n = fminf(fmaxf(nz * sp.noise_sigma, -sp.noise_clip), sp.noise_clip);
-          x = fminf(fmaxf(x + n, -1.f), 1.f);
+      float* cptr = sp.C + (long long)g * sp.c_gs + (long long)row_base * sp.c_ld + col;
+      if (col_ok) {
+        for (int rr = 0; rr < nrows; ++rr) {
+          *cptr = act_forward(st[rr * 33 + lane] + bias, sp.act);
+          cptr += sp.c_ld;
         }
-        sp.C[(long long)g * sp.c_gs + (long long)row * sp.c_ld + col] = x;
       }
     } else if (MODE == kDgrad) {
-      for (int rr = 0; rr < nrows; ++rr) {
-        if (!col_ok) continue;
-        const int row = row_base + rr;
-        float* cptr = sp.C + (long long)g * sp.c_gs + (long long)row * sp.c_ld + col;
-        float x = st[rr * 33 + lane];
-        if (sp.accumulate) x += *cptr;
-        if (sp.aux) x *= act_backward(sp.aux[(long long)g * sp.aux_gs + (long long)row * sp.aux_ld + col], sp.act);
-        *cptr = x;
+      float* cbase = sp.C + (long long)g * sp.c_gs + (long long)row_base * sp.c_ld + col;
+      const float* hbase = sp.aux ? sp.aux + (long long)g * sp.aux_gs + (long long)row_base * sp.aux_ld + col : nullptr;
+      const bool acc_in = sp.accumulate != 0;
+      for (int r0 = 0; r0 < nrows; r0 += U) {
+        float hv[U], cv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const bool ok = col_ok && r0 + u < nrows;
+          hv[u] = (hbase && ok) ? hbase[(long long)(r0 + u) * sp.aux_ld] : 0.f;
+          cv[u] = (acc_in && ok) ? cbase[(long long)(r0 + u) * sp.c_ld] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (col_ok && r0 + u < nrows) {
+            float x = st[(r0 + u) * 33 + lane] + cv[u];
+            if (hbase) x *= act_backward(hv[u], sp.act);
+            cbase[(long long)(r0 + u) * sp.c_ld] = x;
+          }
+        }
       }
     } else {
       AdamScalars sc;
       if (sp.P) sc = *sp.adam;
-      for (int rr = 0; rr < nrows; ++rr) {
-        if (!col_ok) continue;
-        const int row = row_base + rr;
-        const float gval = st[rr * 33 + lane];
+      const long long poff = (long long)g * sp.p_gs + (long long)row_base * sp.p_ld + col;
+      float* cbase = sp.C ? sp.C + (long long)g * sp.c_gs + (long long)row_base * sp.c_ld + col : nullptr;
+      for (int r0 = 0; r0 < nrows; r0 += U) {
+        float pv[U], mv[U], vv[U];
         if (sp.P) {
-          const long long off = (long long)g * sp.p_gs + (long long)row * sp.p_ld + col;
-          float pv = sp.P[off], mv = sp.M[off], vv = sp.V[off];
-          adam_update(gval, pv, mv, vv, sc);
-          sp.P[off] = pv;
-          sp.M[off] = mv;
-          sp.V[off] = vv;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const bool ok = col_ok && r0 + u < nrows;
+            const long long o = poff + (long long)(r0 + u) * sp.p_ld;
+            pv[u] = ok ? sp.P[o] : 0.f;
+            mv[u] = ok ? sp.M[o] : 0.f;
+            vv[u] = ok ? sp.V[o] : 0.f;
+          }
         }
-        if (sp.C) sp.C[(long long)g * sp.c_gs + (long long)row * sp.c_ld + col] = gval;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (col_ok && r0 + u < nrows) {
+            const float gval = st[(r0 + u) * 33 + lane];
+            if (sp.P) {
+              const long long o = poff + (long long)(r0 + u) * sp.p_ld;
+              adam_update(gval, pv[u], mv[u], vv[u], sc);
+              sp.P[o] = pv[u];
+              sp.M[o] = mv[u];
+              sp.V[o] = vv[u];
+            }
+            if (cbase) cbase[(long long)(r0 + u) * sp.c_ld] = gval;
+          }
+        }
       }
     }
     __syncwarp();
@@ -365,7 +399,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) gemm_tc_kernel(const __grid_con
 }
 
 inline bool tc_eligible(const GemmProblem& p) {
-  if (p.I % kTcM != 0 || p.J < 64 || p.J > kTcNMax || (p.J % 16) != 0) return false;
+  if (p.I % kTcM != 0 || p.J < 64 || p.J > kTcNMax || (p.J % 16) != 0 || p.act == kActTanhNoise) return false;
   for (int s = 0; s < p.nseg; ++s)
     if (p.seg[s].b_ones) return false;
   return true;

@@ -1,5 +1,6 @@
 // host.cuh -- host-side plumbing: error string, device buffers, launch tables, launchers.
 #pragma once
+#include <algorithm>
 #include <cstdlib>
 #include <mutex>
 #include <vector>
@@ -103,6 +104,14 @@ inline int gemm_table_upload(GemmTable* t, int mode, std::vector<GemmProblem>& p
     ff.push_back(p);
   }
   (void)want_tc;
+  // longest reductions first: their CTAs are scheduled in the first wave and the short problems fill in behind
+  auto chunks_of = [](const GemmProblem& p) {
+    int c = 0;
+    for (int s = 0; s < p.nseg; ++s) c += ceil_div(p.seg[s].len, kBK);
+    return c;
+  };
+  std::stable_sort(ff.begin(), ff.end(), [&](const GemmProblem& a, const GemmProblem& b) { return chunks_of(a) > chunks_of(b); });
+  std::stable_sort(tc.begin(), tc.end(), [&](const GemmProblem& a, const GemmProblem& b) { return chunks_of(a) > chunks_of(b); });
   int tiles = 0;
   for (auto& p : ff) {
     p.tile_begin = tiles;
@@ -228,10 +237,15 @@ struct Fork {
   std::vector<cudaStream_t> side;
   std::vector<cudaEvent_t> events;
   size_t next_event = 0;
-  int init(cudaStream_t main_stream, int nside, int nevents) {
+  // side streams listed in `low_priority_mask` carry work with slack (encoder step, hoisted actor forward):
+  // captured kernel nodes inherit the stream priority, so the critical chain gets the SMs first
+  int init(cudaStream_t main_stream, int nside, int nevents, unsigned low_priority_mask = 0) {
     main = main_stream;
     side.resize(nside);
-    for (auto& s : side) B200_CHECK_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    int least = 0, greatest = 0;
+    B200_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    for (int i = 0; i < nside; ++i)
+      B200_CHECK_CUDA(cudaStreamCreateWithPriority(&side[i], cudaStreamNonBlocking, ((low_priority_mask >> i) & 1u) ? least : greatest));
     events.resize(nevents);
     for (auto& e : events) B200_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return kOk;

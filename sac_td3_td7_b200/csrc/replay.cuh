@@ -75,6 +75,7 @@ struct SampleArgs {
   int spw;  // samples per warp
 };
 
+#define PFX(i) ((i) + ((i) >> 4))
 __global__ void __launch_bounds__(256) lap_sample_kernel(SampleArgs a) {
   B200_DYN_SMEM(double, prefix);  // [ntiles] inclusive tile prefix sums (prioritized mode)
   __shared__ double warp_tot[8];
@@ -87,18 +88,19 @@ __global__ void __launch_bounds__(256) lap_sample_kernel(SampleArgs a) {
     // a contiguous run, warp/block scan of the run totals, add the offsets back
     const int nt = a.ntiles;
     const double* ts = a.tile_sums + (long long)g * a.ts_gs;
-    for (int t = tid; t < nt; t += 256) prefix[t] = ts[t];
+    // (element i lives at PFX(i) = i + i/16: one pad slot per 16 keeps the per-thread runs off a single bank)
+    for (int t = tid; t < nt; t += 256) prefix[PFX(t)] = ts[t];
     __syncthreads();
     const int per = (nt + 255) / 256;
     const int lo = min(tid * per, nt), hi = min(lo + per, nt);
     double local = 0.0;
-    for (int t = lo; t < hi; ++t) { local += prefix[t]; prefix[t] = local; }
+    for (int t = lo; t < hi; ++t) { local += prefix[PFX(t)]; prefix[PFX(t)] = local; }
     const double incl = warp_inclusive_scan(local, lane);
     if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
     double off = incl - local;
     for (int w = 0; w < warp; ++w) off += warp_tot[w];
-    for (int t = lo; t < hi; ++t) prefix[t] += off;
+    for (int t = lo; t < hi; ++t) prefix[PFX(t)] += off;
     __syncthreads();
   }
 
@@ -121,16 +123,16 @@ __global__ void __launch_bounds__(256) lap_sample_kernel(SampleArgs a) {
   long long idx;
   if (a.prioritized) {
     const int nt = a.ntiles;
-    const float total32 = (float)prefix[nt - 1];
+    const float total32 = (float)prefix[PFX(nt - 1)];
     const float v = __fmul_rn(u, total32);
     // first tile whose fp32-rounded inclusive prefix reaches v
     int lo = 0, hi = nt - 1;
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
-      if ((float)prefix[mid] >= v) hi = mid; else lo = mid + 1;
+      if ((float)prefix[PFX(mid)] >= v) hi = mid; else lo = mid + 1;
     }
     const int tile = lo;
-    const double base = tile > 0 ? prefix[tile - 1] : 0.0;
+    const double base = tile > 0 ? prefix[PFX(tile - 1)] : 0.0;
     const float* p = a.priority + (long long)g * a.prio_gs + (long long)tile * kPrioTile + lane * 8;
     const float4 x0 = *reinterpret_cast<const float4*>(p);
     const float4 x1 = *reinterpret_cast<const float4*>(p + 4);
@@ -247,7 +249,7 @@ struct Replay {
     row_stride = (int)round_up(2 * S + A + 2, 4);
     cap_pad = round_up(capacity, kPrioTile * kPrioTilesPerCta);
     max_tiles = (int)(cap_pad / kPrioTile);
-    B200_REQUIRE((size_t)max_tiles * sizeof(double) <= 200 * 1024, "replay: capacity too large for the shared-memory tile scan (max ~26M rows)");
+    B200_REQUIRE((size_t)(max_tiles + max_tiles / 16 + 1) * sizeof(double) <= 200 * 1024, "replay: capacity too large for the shared-memory tile scan (max ~26M rows)");
     const long long row_sets = share_rows ? 1 : groups;
     B200_TRY(arena.alloc(&d_rows, (size_t)row_sets * capacity * row_stride));
     B200_TRY(arena.alloc(&d_idx, (size_t)groups * max_batch));
@@ -337,7 +339,7 @@ struct Replay {
     a.prioritized = prioritized ? 1 : 0;
     a.spw = samples_per_warp(groups);
     dim3 grid((unsigned)ceil_div(B, 8 * a.spw), (unsigned)groups), block(256);
-    const size_t smem = prioritized ? (size_t)ntiles * sizeof(double) : 0;
+    const size_t smem = prioritized ? (size_t)(ntiles + ntiles / 16 + 1) * sizeof(double) : 0;
     B200_LAUNCH(lap_sample_kernel, grid, block, smem, stream, a);
     B200_CHECK_LAUNCH();
     last_batch = B;
