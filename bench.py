@@ -75,6 +75,8 @@ def cpu_updates_per_s(workload: str, budget_s: float, steps: int | None = None, 
     from oracle import replay as oreplay
 
     algo, env, prio, _, rows = WORKLOADS[workload]
+    # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1 to its workers)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     torch.manual_seed(0)
     agent = {"TD7": oagents.OracleTD7, "TD3": oagents.OracleTD3, "SAC": oagents.OracleSAC}[algo](env, use_lap=prio)
     buf = (oreplay.OracleLAP if prio else oreplay.OracleUniform)(rows, env)
