@@ -48,7 +48,7 @@ for mode in (0, 1, 2):
     for nprob in (1, 2, 5):
         for K in (256, 768):
             row = []
-            for sk in (1, 2, 3, 4, 6):
+            for sk in (1, 2, 3, 4):
                 row.append(f"{launch(mode, nprob, K, sk):6.2f}")
             print(mode, nprob, K, " ".join(row), flush=True)
 # empty-ish kernel cost reference: K=64 single chunk

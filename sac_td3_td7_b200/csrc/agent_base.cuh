@@ -12,6 +12,7 @@ constexpr int kInfoRing = 1024;  // update steps whose losses stay readable with
 // (then the buffer already holds caller-provided noise -- parity tests).
 __global__ void __launch_bounds__(256) gauss_fill_kernel(float* __restrict__ out_base, long long gs, long long n, unsigned long long seed0, int stream_id,
                                                          const int* __restrict__ step_counter, const int* __restrict__ inject) {
+  B200_PDL_PROLOGUE();
   if (*inject) return;
   const long long pair = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pair * 2 >= n) return;
@@ -33,6 +34,7 @@ struct StageArgs {
   int B, S, A;
 };
 __global__ void __launch_bounds__(256) stage_batch_kernel(StageArgs a) {
+  B200_PDL_PROLOGUE();
   const int nS = a.B * a.S, nA = a.B * a.A;
   const int total = 2 * nS + nA + 2 * a.B;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {

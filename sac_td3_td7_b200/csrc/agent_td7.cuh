@@ -12,6 +12,7 @@
 namespace b200rl {
 
 __global__ void td7_range_sync_kernel(TD7Range* r, int G) {
+  B200_PDL_PROLOGUE();
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g < G) { r[g].value_target_max = r[g].value_max; r[g].value_target_min = r[g].value_min; }
 }
@@ -278,11 +279,13 @@ struct TD7Agent : AgentBase {
     B200_TRY(launch_gauss(noise, 0, sP));
     // ---- encoder branch
     B200_TRY(fork.link(M, sE));
+    if (getenv("B200RL_DEBUG_SKIP_ENCODER") == nullptr) {  // (measurement knob: how much does the side branch cost the critical chain?)
     GL(E[0], sE); GL(E[1], sE); GL(E[2], sE); RL(En[0], sE);
     GL(E[3], sE); GL(E[4], sE); GL(E[5], sE);
     B200_TRY(fork.link(sP, sE));  // info slot (loss) and Adam scalars (wgrad)
     B200_TRY(launch_enc_loss(sE));
     GL(E[6], sE); GL(E[7], sE); GL(E[8], sE); RL(En[1], sE); GL(E[9], sE); GL(E[10], sE); GL(E[11], sE);
+    }
     // ---- critic chain
     GL(actor ? C[1] : C[0], M);
     B200_TRY(fork.link(M, sN));

@@ -539,6 +539,12 @@ int b200rl_op_gemm(int mode, const b200rl_gemm_problem* problems_host, int nprob
   B200_CHECK_CUDA(cudaStreamSynchronize(as_stream(stream)));
   return kOk;
 }
+#ifdef B200RL_PROBE
+int b200rl_debug_probe(long long* out64x10) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out64x10, g_probe, sizeof(long long) * 640) == cudaSuccess ? 0 : 1;
+}
+#endif
 int b200rl_op_gemm_timed(int mode, const b200rl_gemm_problem* problems_host, int nproblems, int groups, int warmup, int iters, float* ms_per_launch, void* stream) {
   B200_REQUIRE(problems_host && nproblems > 0 && groups > 0 && iters > 0 && ms_per_launch, "bad arguments");
   B200_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0..2");

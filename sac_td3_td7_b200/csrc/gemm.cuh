@@ -96,21 +96,55 @@ struct GemmProblem {
   int tiles_j;
 };
 
-// One launch: the problem table travels in kernel-parameter (constant) memory, so a CTA finds its
-// problem without a dependent global load.  With splitk > 1 every output tile is computed by `splitk`
-// CTAs, each over a contiguous slice of the reduction chunks; the partial tiles meet in `scratch` and the
-// CTA that arrives last (ticket counter) sums them in split order -- so the result does not depend on
-// arrival order -- and runs the epilogue.  Splitting is what gives a single agent's 64-tile layers
-// enough CTAs to occupy the machine and cuts the serial chunk chain per CTA.
-constexpr int kMaxProblems = 24;
+// One launch of the tcgen05 kernel (gemm_tc.cuh): the problem table travels in kernel-parameter (constant)
+// memory, so a CTA finds its problem without a dependent global load.
+#ifndef B200RL_MAX_PROBLEMS
+#define B200RL_MAX_PROBLEMS 24
+#endif
+constexpr int kMaxProblems = B200RL_MAX_PROBLEMS;
 struct GemmLaunch {
   GemmProblem p[kMaxProblems];
   int nprob;
-  int splitk;
   int total_tiles;
+};
+
+// Device-side form of a problem for the FFMA kernel: GemmProblem plus everything the host can work out
+// once (chunk counts, the split of the reduction, a reciprocal for the tile -> (row, col) division), so the
+// per-CTA setup is a handful of constant loads.
+struct FfmaProblem {
+  GemmSeg seg[3];
+  int nseg, I, J;
+  int total_chunks;        // sum over segments of ceil(len / kBK)
+  int per_split;           // chunks handled by each of the `splitk` CTAs of a tile
+  int tile_begin, tiles_j;
+  unsigned tiles_j_magic;  // floor(2^32 / tiles_j) + 1 for tiles_j > 1 (exact quotient for the tile counts used here)
+  float* C;
+  long long c_gs;
+  int c_ld, act;
+  const float* bias;
+  long long bias_gs;
+  const float* aux;
+  long long aux_gs;
+  int aux_ld, accumulate;
+  float* P;
+  float* M;
+  float* V;
+  long long p_gs;
+  int p_ld;
+  float noise_sigma, noise_clip;
   int pad;
-  float* scratch;      // [groups][total_tiles][splitk][32*32]
-  unsigned* tickets;   // [groups][total_tiles], zero between launches
+  const AdamScalars* adam;
+};
+// With splitk > 1 the kernel is launched in thread-block clusters of `splitk` CTAs: the CTAs of a cluster
+// compute the same output tile over disjoint, contiguous slices of the reduction chunks, the non-leaders
+// push their partial tiles into the leader's shared memory (DSMEM) and the leader sums them in rank order
+// -- deterministic, no global scratch, no atomics -- and runs the epilogue.  This is what lets a single
+// agent's 64-tile layers occupy the whole machine and shortens the serial chunk chain per CTA.
+constexpr int kMaxSplitK = 4;
+struct FfmaLaunch {
+  FfmaProblem p[kMaxProblems];
+  int nprob;
+  int splitk;
 };
 
 constexpr int kTile = 32;   // output tile edge
@@ -119,18 +153,11 @@ constexpr int kGemmThreads = 256;
 constexpr int kStages = 3;
 constexpr int kTileElems = kTile * kTile;          // one partial output tile
 constexpr int kStageElems = 2 * kTile * kBK;       // A tile + B tile of one stage
-constexpr int kGemmSmemBytes = kStages * kStageElems * (int)sizeof(float);  // 48 KB (>= 8 partial tiles = 32 KB)
+constexpr int kPipeBytes = kStages * kStageElems * (int)sizeof(float);  // 48 KB (>= 8 partial tiles = 32 KB)
+// + one 4 KB receive slot per non-leader CTA of a split-K cluster
+constexpr int gemm_smem_bytes(int splitk) { return kPipeBytes + (splitk - 1) * kTileElems * (int)sizeof(float); }
 
 __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-
-// L2-coherent 128-bit load (bypasses the non-coherent L1): data written by other CTAs of this launch
-__device__ __forceinline__ float4 ld_cg_f4(const float* p) {
-#ifdef B200_EMU
-  return *reinterpret_cast<const float4*>(p);
-#else
-  return __ldcg(reinterpret_cast<const float4*>(p));
-#endif
-}
 
 // ---- cp.async (LDGSTS) helpers; under host emulation they degrade to plain copies ----
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
@@ -158,56 +185,56 @@ __device__ __forceinline__ void cp_async_wait() {
 //   K-major (operand contiguous along the reduction r in global): row = c, 16 float4 slots along r,
 //     slot index XOR (c >> 2) & 7 so the strided per-lane float4 reads hit 8 distinct bank groups;
 //   C-major (operand contiguous along the output index c in global): row = r, 8 float4 slots along c.
-// Everything that does not change from chunk to chunk (row validity, alignment, base pointers, the
+// Everything that does not change from chunk to chunk (row validity, alignment, base pointer, the
 // shared-memory offset) is computed once per segment; per chunk the fast path is one bounds test,
-// one cp.async and one pointer bump per strip.
+// one cp.async per strip and one pointer bump.  The second strip sits 16 rows (K-major) / 32 rows
+// (C-major) below the first, so one pointer, one stride and one offset describe both.
 template <bool KMAJOR>
 struct OperandCursor {
-  const float* src[2];
-  int dst[2];        // float offset inside the operand tile
+  const float* src;  // strip 0 of the next chunk; strip 1 = src + delta
+  int delta;         // K-major: 16 * ld; C-major: 32 * ld
+  int dst;           // float offset of strip 0 inside the operand tile
   int pos;           // K-major: r offset of the strip inside the chunk (4*s); C-major: c0 + 4*s
-  int row[2];        // C-major: r offset of the strip inside the chunk
-  bool row_ok[2];    // K-major: output row inside the problem
-  bool fast[2];      // 16-byte aligned source and (C-major) complete strip
-  long long bump;    // pointer advance per chunk
+  int row;           // C-major: r offset of strip 0 inside the chunk (strip 1: + 32)
+  bool ok0, ok1;     // K-major: output row of strip 0 / 1 inside the problem; C-major: strip has >= 1 valid column
+  bool vec;          // 16-byte aligned source (and, C-major, a complete strip): cp.async path
 
   __device__ __forceinline__ void init(const float* base, int ld, int c0, int cmax, int tid, int r_start) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (KMAJOR) {
-        const int c = (tid >> 4) + 16 * h, s = tid & 15;
-        dst[h] = c * kBK + ((s ^ ((c >> 2) & 7)) << 2);
-        pos = s << 2;
-        row[h] = 0;
-        row_ok[h] = (c0 + c) < cmax;
-        src[h] = base + (long long)(c0 + c) * ld + pos + r_start;
-        fast[h] = row_ok[h] && aligned16(src[h]);
-        bump = kBK;
-      } else {
-        const int r = (tid >> 3) + 32 * h, s = tid & 7;
-        dst[h] = r * kTile + (s << 2);
-        pos = c0 + (s << 2);
-        row[h] = r;
-        row_ok[h] = true;
-        src[h] = base + (long long)(r_start + r) * ld + pos;
-        fast[h] = (pos + 3 < cmax) && aligned16(src[h]);
-        bump = (long long)kBK * ld;
-      }
+    if (KMAJOR) {
+      const int c = tid >> 4, s = tid & 15;
+      dst = c * kBK + ((s ^ ((c >> 2) & 7)) << 2);
+      pos = s << 2;
+      row = 0;
+      ok0 = (c0 + c) < cmax;
+      ok1 = (c0 + c + 16) < cmax;
+      src = base + (long long)(c0 + c) * ld + (pos + r_start);
+      delta = 16 * ld;
+      vec = aligned16(src);  // 16*ld floats and the 64-float bump keep the alignment
+    } else {
+      const int r = tid >> 3, s = tid & 7;
+      dst = r * kTile + (s << 2);
+      pos = c0 + (s << 2);
+      row = r;
+      ok0 = ok1 = pos < cmax;
+      src = base + (long long)(r_start + r) * ld + pos;
+      delta = 32 * ld;
+      vec = (pos + 3 < cmax) && aligned16(src);
     }
   }
   // copy this thread's strips of the chunk starting at reduction offset r0 (segment length rlen)
   __device__ __forceinline__ void stage(float* tile, int r0, int rlen, int cmax) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      float* d = tile + dst[h];
+      const float* q = src + (h ? delta : 0);
       if (KMAJOR) {
+        float* d = tile + (h ? ((dst ^ 16) + 16 * kBK) : dst);
         const int p = r0 + pos;
-        if (fast[h] && p + 3 < rlen) {
-          cp_async16(d, src[h]);
+        const bool ok = h ? ok1 : ok0;
+        if (vec && ok && p + 3 < rlen) {
+          cp_async16(d, q);
         } else {
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row_ok[h] && p < rlen) {
-            const float* q = src[h];
+          if (ok && p < rlen) {
             v.x = q[0];
             if (p + 1 < rlen) v.y = q[1];
             if (p + 2 < rlen) v.z = q[2];
@@ -216,13 +243,13 @@ struct OperandCursor {
           *reinterpret_cast<float4*>(d) = v;
         }
       } else {
-        const bool in = (r0 + row[h]) < rlen;
-        if (fast[h] && in) {
-          cp_async16(d, src[h]);
+        float* d = tile + dst + h * (32 * kTile);
+        const bool in = (r0 + row + 32 * h) < rlen;
+        if (vec && in) {
+          cp_async16(d, q);
         } else {
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (in && pos < cmax) {
-            const float* q = src[h];
+          if (in && ok0) {
             v.x = q[0];
             if (pos + 1 < cmax) v.y = q[1];
             if (pos + 2 < cmax) v.z = q[2];
@@ -231,8 +258,8 @@ struct OperandCursor {
           *reinterpret_cast<float4*>(d) = v;
         }
       }
-      src[h] += bump;
     }
+    src += KMAJOR ? (long long)kBK : 2ll * delta;
   }
 };
 
@@ -265,25 +292,93 @@ __device__ __forceinline__ float act_backward(float h, int act) {
   }
 }
 
+// Optional in-kernel timeline (build with -DB200RL_PROBE): CTA (0,0) thread 0 records the global
+// timer at entry / exit and the SM clock at the phase boundaries of every launch into a ring.
+#ifdef B200RL_PROBE
+__device__ long long g_probe[64][10];
+__device__ unsigned g_probe_n;
+#define B200_PROBE_DECL long long pb_[10]; const bool pb_on_ = (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0); if (pb_on_) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pb_[0])); pb_[1] = clock64(); }
+#define B200_PROBE(i) if (pb_on_) pb_[i] = clock64();
+#define B200_PROBE_END if (pb_on_) { pb_[8] = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pb_[9])); unsigned sl_ = atomicAdd(&g_probe_n, 1u) & 63u; for (int q_ = 0; q_ < 10; ++q_) g_probe[sl_][q_] = pb_[q_]; }
+#else
+#define B200_PROBE_DECL
+#define B200_PROBE(i)
+#define B200_PROBE_END
+#endif
+
+// ---- thread-block cluster helpers (split-K through distributed shared memory) ----
+#ifndef B200_EMU
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned cluster_id_x() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// store 16 bytes into the shared memory of CTA `rank` of this cluster, at the address `local` has in ours
+__device__ __forceinline__ void st_cluster_f4(float* local, unsigned rank, float a, float b, float c, float d) {
+  const unsigned la = (unsigned)__cvta_generic_to_shared(local);
+  unsigned ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+#endif
+
+// four consecutive floats of an epilogue operand, all loads in flight at once
+__device__ __forceinline__ void load_quad(float (&o)[4], const float* p, int nvalid) {
+  if (nvalid == 4 && aligned16(p)) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = (e < nvalid) ? p[e] : 0.f;
+  }
+}
+__device__ __forceinline__ void store_quad(float* p, const float (&o)[4], int nvalid) {
+  if (nvalid == 4 && aligned16(p)) {
+    *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (e < nvalid) p[e] = o[e];
+  }
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_constant__ GemmLaunch L) {
+__global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_constant__ FfmaLaunch L) {
+  B200_PDL_PROLOGUE();
+  B200_PROBE_DECL
   constexpr bool A_KM = (MODE != kWgrad);  // A contiguous along the reduction in global memory
   constexpr bool B_KM = (MODE == kFwd);
-  // 3 pipeline stages x (A tile 32x64, B tile 32x64) = 48 KB; the first 32 KB later hold the 8 partial tiles
+  // 3 pipeline stages x (A tile 32x64, B tile 32x64) = 48 KB; the first 32 KB later hold the 8 partial tiles;
+  // behind them one 4 KB receive slot per non-leader CTA of the split-K cluster
   B200_DYN_SMEM(float, smem);
-  __shared__ unsigned s_ticket;
 
   const int tid = threadIdx.x;
   const int g = blockIdx.y;
+  int tile_id = (int)blockIdx.x, split = 0;
+#ifndef B200_EMU
   const int splitk = L.splitk;
-  const int tile_id = (int)blockIdx.x / splitk;
-  const int split = (int)blockIdx.x - tile_id * splitk;
+  if (splitk > 1) {
+    cluster_arrive();  // phase 1: "my shared memory exists" (waited on just before the DSMEM pushes)
+    tile_id = (int)cluster_id_x();
+    split = (int)cluster_ctarank();
+  }
+#else
+  constexpr int splitk = 1;
+#endif
   int pi = 0;
   while (pi + 1 < L.nprob && tile_id >= L.p[pi + 1].tile_begin) ++pi;
-  const GemmProblem& sp = L.p[pi];
+  const FfmaProblem& sp = L.p[pi];
   const int t_local = tile_id - sp.tile_begin;
-  const int i0 = (t_local / sp.tiles_j) * kTile;
-  const int j0 = (t_local % sp.tiles_j) * kTile;
+  const int ti = sp.tiles_j > 1 ? (int)__umulhi((unsigned)t_local, sp.tiles_j_magic) : t_local;
+  const int i0 = ti * kTile;
+  const int j0 = (t_local - ti * sp.tiles_j) * kTile;
   const int I = sp.I, J = sp.J;
 
   const int warp = tid >> 5, lane = tid & 31;
@@ -295,12 +390,9 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_cons
 #pragma unroll
     for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
 
-  int total_chunks = 0;
-  for (int s = 0; s < sp.nseg; ++s) total_chunks += (sp.seg[s].len + kBK - 1) / kBK;
   // this CTA's slice of the flattened (segment, chunk) sequence
-  const int per_split = (total_chunks + splitk - 1) / splitk;
-  const int c_begin = min(split * per_split, total_chunks);
-  const int nchunks = min(c_begin + per_split, total_chunks) - c_begin;
+  const int c_begin = split * sp.per_split;
+  const int nchunks = max(0, min(sp.per_split, sp.total_chunks - c_begin));
 
   // producer cursor
   OperandCursor<A_KM> ca;
@@ -325,8 +417,8 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_cons
     if (pr0 >= plen && ++pseg < sp.nseg) open_segment(0);
   };
   if (nchunks > 0) {
-    int skip = c_begin;  // walk to the segment that holds chunk c_begin
-    for (;;) {
+    int skip = c_begin;  // walk to the segment that holds chunk c_begin (split 0: no iterations)
+    while (skip > 0) {
       const int sc = (sp.seg[pseg].len + kBK - 1) / kBK;
       if (skip < sc) break;
       skip -= sc;
@@ -334,6 +426,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_cons
     }
     open_segment(skip * kBK);
   }
+  B200_PROBE(2)
 
   // prologue: fill kStages-1 stages
 #pragma unroll
@@ -341,10 +434,12 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_cons
     if (s < nchunks) issue(s);
     cp_async_commit();
   }
+  B200_PROBE(3)
 
   for (int c = 0; c < nchunks; ++c) {
     cp_async_wait<kStages - 2>();  // chunk c has landed (this thread's copies)
     __syncthreads();               // ... and everybody's; also: the stage refilled below is no longer being read
+    if (c == 0) { B200_PROBE(4) }
     if (c + kStages - 1 < nchunks) issue((c + kStages - 1) % kStages);
     cp_async_commit();
 
@@ -391,8 +486,42 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_cons
           for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(av[a][rr], bv[b][rr], acc[a][b]);
     }
   }
+
+  // ---- epilogue operands: every load is issued here, before the reduction, so that their L2 round trips
+  // overlap the barriers below instead of being paid one after the other at the end ----
+  const int oi = tid >> 3, oslot = tid & 7;
+  const int gi = i0 + oi;
+  const int gj0 = j0 + oslot * 4;
+  const bool live = (split == 0) && gi < I && gj0 < J;  // this thread writes outputs
+  const int nvalid = live ? min(4, J - gj0) : 0;
+  float e0[4] = {0.f, 0.f, 0.f, 0.f}, e1[4] = {0.f, 0.f, 0.f, 0.f}, e2[4] = {0.f, 0.f, 0.f, 0.f};
+  const int act = sp.act;
+  bool has0 = false, has1 = false;
+  AdamScalars adam_s = {};
+  if (MODE == kFwd) {
+    has0 = sp.bias != nullptr;
+    has1 = act == kActTanhNoise;
+    if (live && has0) load_quad(e0, sp.bias + (long long)g * sp.bias_gs + gj0, nvalid);
+    if (live && has1) load_quad(e1, sp.aux + (long long)g * sp.aux_gs + (long long)gi * sp.aux_ld + gj0, nvalid);
+  } else if (MODE == kDgrad) {
+    has0 = sp.aux != nullptr;
+    has1 = sp.accumulate != 0;
+    if (live && has0) load_quad(e0, sp.aux + (long long)g * sp.aux_gs + (long long)gi * sp.aux_ld + gj0, nvalid);
+    if (live && has1) load_quad(e1, sp.C + (long long)g * sp.c_gs + (long long)gi * sp.c_ld + gj0, nvalid);
+  } else {
+    has0 = sp.P != nullptr;
+    if (live && has0) {
+      const long long off = (long long)g * sp.p_gs + (long long)gi * sp.p_ld + gj0;
+      load_quad(e0, sp.P + off, nvalid);
+      load_quad(e1, sp.M + off, nvalid);
+      load_quad(e2, sp.V + off, nvalid);
+      adam_s = *sp.adam;
+    }
+  }
+
   cp_async_wait<0>();
   __syncthreads();  // everyone is done reading the pipeline stages: reuse the memory for the partial tiles
+  B200_PROBE(5)
 
   // ---- cross-warp reduction of the eight K-slices, fixed order (bit-reproducible) ----
   // partial tile layout: [warp][row][8 slots of float4], slot index XOR (row >> 2) to spread banks
@@ -405,7 +534,6 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_cons
     *reinterpret_cast<float4*>(base + (((2 * lj + 1) ^ li) << 2)) = make_float4(acc[a][4], acc[a][5], acc[a][6], acc[a][7]);
   }
   __syncthreads();
-  const int oi = tid >> 3, oslot = tid & 7;
   float out[4];
   {
     const float* p0 = part + oi * kTile + ((oslot ^ ((oi >> 2) & 7)) << 2);
@@ -417,93 +545,80 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_cons
     }
     out[0] = s.x; out[1] = s.y; out[2] = s.z; out[3] = s.w;
   }
+#ifndef B200_EMU
   if (splitk > 1) {
-    // publish this split's partial tile, take a ticket; the last arriver sums all splits in split order
-    const long long tile_lin = (long long)g * L.total_tiles + tile_id;
-    float* mine = L.scratch + (tile_lin * splitk + split) * kTileElems;
-    *reinterpret_cast<float4*>(mine + tid * 4) = make_float4(out[0], out[1], out[2], out[3]);
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_ticket = atomicAdd(&L.tickets[tile_lin], 1u);
-    __syncthreads();
-    if (s_ticket != (unsigned)(splitk - 1)) return;
-    __threadfence();
-    const float* all = L.scratch + tile_lin * splitk * kTileElems + tid * 4;
-    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = 0; k < splitk; ++k) {
-      const float4 v = ld_cg_f4(all + (long long)k * kTileElems);
-      s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+    // non-leaders push their partial tile into the leader's receive slot; the leader adds them in rank order
+    float* recv = smem + kStages * kStageElems;
+    cluster_wait();  // phase 1 complete: every CTA of the cluster is running
+    if (split != 0) st_cluster_f4(recv + (split - 1) * kTileElems + tid * 4, 0u, out[0], out[1], out[2], out[3]);
+    cluster_arrive();  // phase 2 (release): my push is visible to whoever waits
+    if (split != 0) return;
+    cluster_wait();
+    for (int k = 1; k < splitk; ++k) {
+      const float4 v = *reinterpret_cast<const float4*>(recv + (k - 1) * kTileElems + tid * 4);
+      out[0] += v.x; out[1] += v.y; out[2] += v.z; out[3] += v.w;
     }
-    out[0] = s4.x; out[1] = s4.y; out[2] = s4.z; out[3] = s4.w;
-    if (tid == 0) L.tickets[tile_lin] = 0u;  // ready for the next launch / graph replay
   }
-  const int gi = i0 + oi;
-  if (gi >= I) return;
-  const int gj0 = j0 + oslot * 4;
-  if (gj0 >= J) return;
-  const int nvalid = min(4, J - gj0);
+#endif
+  B200_PROBE(6)
+  if (!live) return;
 
   if (MODE == kFwd) {
-    const float* bias = sp.bias ? sp.bias + (long long)g * sp.bias_gs : nullptr;
-    const float* noise = (sp.act == kActTanhNoise) ? sp.aux + (long long)g * sp.aux_gs + (long long)gi * sp.aux_ld : nullptr;
+    if (has0) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      if (e < nvalid) {
-        float v = out[e] + (bias ? bias[gj0 + e] : 0.f);
-        v = act_forward(v, sp.act);
-        if (noise) {
-          float n = fminf(fmaxf(noise[gj0 + e] * sp.noise_sigma, -sp.noise_clip), sp.noise_clip);
-          v = fminf(fmaxf(v + n, -1.f), 1.f);
+      for (int e = 0; e < 4; ++e) out[e] += e0[e];
+    }
+    switch (act) {
+      case kActRelu:
+#pragma unroll
+        for (int e = 0; e < 4; ++e) out[e] = out[e] > 0.f ? out[e] : 0.f;
+        break;
+      case kActElu:
+#pragma unroll
+        for (int e = 0; e < 4; ++e) out[e] = out[e] > 0.f ? out[e] : expm1f(out[e]);
+        break;
+      case kActTanh:
+#pragma unroll
+        for (int e = 0; e < 4; ++e) out[e] = tanhf(out[e]);
+        break;
+      case kActTanhNoise:
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float n = fminf(fmaxf(e1[e] * sp.noise_sigma, -sp.noise_clip), sp.noise_clip);
+          out[e] = fminf(fmaxf(tanhf(out[e]) + n, -1.f), 1.f);
         }
-        out[e] = v;
-      }
+        break;
+      default: break;
     }
   } else if (MODE == kDgrad) {
-    float* Cg = sp.C + (long long)g * sp.c_gs + (long long)gi * sp.c_ld;
-    const float* H = sp.aux ? sp.aux + (long long)g * sp.aux_gs + (long long)gi * sp.aux_ld : nullptr;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      if (e < nvalid) {
-        float v = out[e];
-        if (sp.accumulate) v += Cg[gj0 + e];
-        if (H) v *= act_backward(H[gj0 + e], sp.act);
-        out[e] = v;
-      }
+      float v = out[e];
+      if (has1) v += e1[e];
+      if (has0) v *= act_backward(e0[e], act);
+      out[e] = v;
     }
   } else {  // kWgrad
-    if (sp.P) {
-      const AdamScalars s = *sp.adam;
-      float* Pp = sp.P + (long long)g * sp.p_gs + (long long)gi * sp.p_ld;
-      float* Mp = sp.M + (long long)g * sp.p_gs + (long long)gi * sp.p_ld;
-      float* Vp = sp.V + (long long)g * sp.p_gs + (long long)gi * sp.p_ld;
+    if (has0) {
+      const long long off = (long long)g * sp.p_gs + (long long)gi * sp.p_ld + gj0;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (e < nvalid) {
-          float p = Pp[gj0 + e], m = Mp[gj0 + e], v = Vp[gj0 + e];
-          adam_update(out[e], p, m, v, s);
-          Pp[gj0 + e] = p;
-          Mp[gj0 + e] = m;
-          Vp[gj0 + e] = v;
-        }
-      }
+      for (int e = 0; e < 4; ++e) adam_update(out[e], e0[e], e1[e], e2[e], adam_s);
+      store_quad(sp.P + off, e0, nvalid);
+      store_quad(sp.M + off, e1, nvalid);
+      store_quad(sp.V + off, e2, nvalid);
     }
     if (!sp.C) return;
   }
-  float* Crow = sp.C + (long long)g * sp.c_gs + (long long)gi * sp.c_ld + gj0;
-  if (nvalid == 4 && aligned16(Crow)) {
-    *reinterpret_cast<float4*>(Crow) = make_float4(out[0], out[1], out[2], out[3]);
-  } else {
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      if (e < nvalid) Crow[e] = out[e];
-  }
+  B200_PROBE(7)
+  store_quad(sp.C + (long long)g * sp.c_gs + (long long)gi * sp.c_ld + gj0, out, nvalid);
+  B200_PROBE_END
 }
 
 // ----------------------------------------------------------------------------- host side
 // A launch table: problems are appended on the host once, then replayed (the struct is passed by value
 // as the kernel parameter; scratch / tickets for split-K live in device memory owned by the table).
 struct GemmTable {
-  GemmLaunch launch;      // problems run by the FFMA kernel
+  FfmaLaunch launch;      // problems run by the FFMA kernel
   GemmLaunch launch_tc;   // problems run by the tcgen05 kernel (stacked seeds; gemm_tc.cuh)
   int nprob = 0;
   int total_tiles = 0;    // FFMA tiles (32 x 32)

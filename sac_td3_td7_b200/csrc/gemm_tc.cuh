@@ -193,6 +193,7 @@ struct TcOperand {
 
 template <int MODE>
 __global__ void __launch_bounds__(kTcThreads, 2) gemm_tc_kernel(const __grid_constant__ GemmLaunch L) {
+  B200_PDL_PROLOGUE();
   constexpr bool A_KM = (MODE != kWgrad);
   constexpr bool B_KM = (MODE == kFwd);
   extern __shared__ __align__(16) unsigned char tc_smem_raw[];

@@ -63,19 +63,49 @@ inline void add_seg(GemmProblem& p, const float* A, int a_ld, long long a_gs, co
   s.b_ones = 0;
 }
 
-// How many CTAs share one output tile.  Measured on B200 (profiles/sweep_gemm.py, graph-timed): a launch
-// costs ~4 us fixed + ~0.76 us per 64-deep chunk per CTA, and the ticket/scratch round trip of a split
-// costs ~1.5-2 us, so splitting only pays for long reductions (K >= 512) of launches that leave most SMs
-// idle (<= 64 tiles); everything else runs unsplit.
+// How many CTAs (one thread-block cluster) share one output tile.  A single agent's layers are 64 tiles of
+// 4-12 serial 64-deep chunks each -- less than half of the 148 SMs busy, on a chain that is pure latency --
+// so the reduction is cut across a cluster while the launch still fits one wave of 2 CTAs per SM and every
+// CTA keeps at least two chunks.  Measured on B200 with profiles/sweep_gemm.py (graph-timed).
+inline int chunks_of(const GemmProblem& p) {
+  int c = 0;
+  for (int s = 0; s < p.nseg; ++s) c += ceil_div(p.seg[s].len, kBK);
+  return c;
+}
 inline int choose_splitk(const std::vector<GemmProblem>& probs, int tiles, int groups) {
+#ifdef B200_EMU
+  (void)probs; (void)tiles; (void)groups;
+  return 1;  // clusters / DSMEM are not emulated
+#else
   int max_chunks = 1;
-  for (const auto& p : probs) {
-    int c = 0;
-    for (int s = 0; s < p.nseg; ++s) c += ceil_div(p.seg[s].len, kBK);
-    max_chunks = std::max(max_chunks, c);
-  }
-  if ((long long)tiles * groups <= 64 && max_chunks >= 8) return 2;
-  return 1;
+  for (const auto& p : probs) max_chunks = std::max(max_chunks, chunks_of(p));
+  const long long ctas = (long long)tiles * groups;
+  // sweep (us per launch, 64 tiles): K=256 -> 5.3 / 4.8 / 4.9 for 1 / 2 / 4 CTAs per tile; K=768 -> 11.5 / 7.8 / 7.3;
+  // at 128 tiles and above splitting no longer pays (the SMs are already issue-bound)
+  int s = 1;
+  if (ctas * 2 <= 148 && max_chunks >= 4) s = 2;
+  if (ctas * 2 <= 148 && max_chunks >= 8) s = 4;
+  return s;
+#endif
+}
+
+inline FfmaProblem make_ffma_problem(const GemmProblem& p, int splitk) {
+  FfmaProblem f;
+  memset(&f, 0, sizeof(f));
+  for (int s = 0; s < 3; ++s) f.seg[s] = p.seg[s];
+  f.nseg = p.nseg; f.I = p.I; f.J = p.J;
+  f.total_chunks = chunks_of(p);
+  f.per_split = ceil_div(f.total_chunks, splitk);
+  f.tile_begin = p.tile_begin;
+  f.tiles_j = p.tiles_j;
+  f.tiles_j_magic = p.tiles_j > 1 ? (unsigned)((1ull << 32) / (unsigned)p.tiles_j) + 1u : 0u;
+  f.C = p.C; f.c_gs = p.c_gs; f.c_ld = p.c_ld; f.act = p.act;
+  f.bias = p.bias; f.bias_gs = p.bias_gs;
+  f.aux = p.aux; f.aux_gs = p.aux_gs; f.aux_ld = p.aux_ld; f.accumulate = p.accumulate;
+  f.P = p.P; f.M = p.M; f.V = p.V; f.p_gs = p.p_gs; f.p_ld = p.p_ld;
+  f.noise_sigma = p.noise_sigma; f.noise_clip = p.noise_clip;
+  f.adam = p.adam;
+  return f;
 }
 
 // Stacked seeds (groups >= kTcMinGroups) run their eligible problems on the tensor cores (TF32);
@@ -105,11 +135,6 @@ inline int gemm_table_upload(GemmTable* t, int mode, std::vector<GemmProblem>& p
   }
   (void)want_tc;
   // longest reductions first: their CTAs are scheduled in the first wave and the short problems fill in behind
-  auto chunks_of = [](const GemmProblem& p) {
-    int c = 0;
-    for (int s = 0; s < p.nseg; ++s) c += ceil_div(p.seg[s].len, kBK);
-    return c;
-  };
   std::stable_sort(ff.begin(), ff.end(), [&](const GemmProblem& a, const GemmProblem& b) { return chunks_of(a) > chunks_of(b); });
   std::stable_sort(tc.begin(), tc.end(), [&](const GemmProblem& a, const GemmProblem& b) { return chunks_of(a) > chunks_of(b); });
   int tiles = 0;
@@ -131,19 +156,19 @@ inline int gemm_table_upload(GemmTable* t, int mode, std::vector<GemmProblem>& p
   t->groups = groups;
   memset(&t->launch, 0, sizeof(t->launch));
   memset(&t->launch_tc, 0, sizeof(t->launch_tc));
-  for (size_t i = 0; i < ff.size(); ++i) t->launch.p[i] = ff[i];
+  if (const char* e = getenv("B200RL_SPLITK")) force_splitk = atoi(e);  // tuning knob (profiles/sweep_gemm.py)
+  int splitk = ff.empty() ? 1 : (force_splitk > 0 ? force_splitk : choose_splitk(ff, tiles, groups));
+#ifdef B200_EMU
+  splitk = 1;
+#endif
+  B200_REQUIRE(splitk >= 1 && splitk <= kMaxSplitK, "split-K factor out of range");
+  (void)arena;
+  for (size_t i = 0; i < ff.size(); ++i) t->launch.p[i] = make_ffma_problem(ff[i], splitk);
   for (size_t i = 0; i < tc.size(); ++i) t->launch_tc.p[i] = tc[i];
   t->launch.nprob = (int)ff.size();
-  t->launch.total_tiles = tiles;
+  t->launch.splitk = splitk;
   t->launch_tc.nprob = (int)tc.size();
   t->launch_tc.total_tiles = tct;
-  t->launch_tc.splitk = 1;
-  if (const char* e = getenv("B200RL_SPLITK")) force_splitk = atoi(e);  // tuning knob (profiles/sweep_gemm.py)
-  t->launch.splitk = ff.empty() ? 1 : (force_splitk > 0 ? force_splitk : choose_splitk(ff, tiles, groups));
-  if (t->launch.splitk > 1) {
-    B200_TRY(arena->alloc(&t->launch.scratch, (size_t)groups * tiles * t->launch.splitk * kTileElems));
-    B200_TRY(arena->alloc(&t->launch.tickets, (size_t)groups * tiles));
-  }
   return kOk;
 }
 
@@ -156,9 +181,9 @@ inline int gemm_table_launch(const GemmTable& t, int groups, cudaStream_t stream
 #ifndef B200_EMU
   static bool attr_set = false;  // > 48 KB of dynamic shared memory needs the opt-in once per kernel
   if (!attr_set) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<kFwd>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
-    B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<kDgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
-    B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<kWgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<kFwd>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(kMaxSplitK)));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<kDgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(kMaxSplitK)));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<kWgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(kMaxSplitK)));
     B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kFwd>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
     B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kDgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
     B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kWgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
@@ -175,11 +200,18 @@ inline int gemm_table_launch(const GemmTable& t, int groups, cudaStream_t stream
   }
 #endif
   if (t.launch.nprob > 0) {
-    dim3 grid((unsigned)(t.total_tiles * t.launch.splitk), (unsigned)groups, 1), block(kGemmThreads, 1, 1);
-    switch (t.mode) {
-      case kFwd: { auto k = gemm_kernel<kFwd>; B200_LAUNCH(k, grid, block, kGemmSmemBytes, stream, t.launch); break; }
-      case kDgrad: { auto k = gemm_kernel<kDgrad>; B200_LAUNCH(k, grid, block, kGemmSmemBytes, stream, t.launch); break; }
-      default: { auto k = gemm_kernel<kWgrad>; B200_LAUNCH(k, grid, block, kGemmSmemBytes, stream, t.launch); break; }
+    const int sk = t.launch.splitk;
+    dim3 grid((unsigned)(t.total_tiles * sk), (unsigned)groups, 1), block(kGemmThreads, 1, 1);
+    const size_t smem = (size_t)gemm_smem_bytes(sk);
+    void (*k)(FfmaLaunch) = t.mode == kFwd ? gemm_kernel<kFwd> : t.mode == kDgrad ? gemm_kernel<kDgrad> : gemm_kernel<kWgrad>;
+#ifndef B200_EMU
+    if (sk > 1) {
+      ++launch_counter();
+      launch_cluster(k, grid, block, smem, stream, (unsigned)sk, t.launch);
+    } else
+#endif
+    {
+      B200_LAUNCH(k, grid, block, smem, stream, t.launch);
     }
     B200_CHECK_LAUNCH();
   }

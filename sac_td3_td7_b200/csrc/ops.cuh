@@ -33,6 +33,7 @@ constexpr float kNormEps = 1e-8f;
 
 template <bool BWD>
 __global__ void __launch_bounds__(256) avgl1norm_kernel(const RowOp* __restrict__ ops, int nops, int total_rows) {
+  B200_PDL_PROLOGUE();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row_lin = blockIdx.x * 8 + warp;
   const int g = blockIdx.y;
@@ -85,6 +86,7 @@ struct StepState {
 
 // one thread: advance counters and refresh the Adam scalars of the optimizers that step now
 __global__ void prep_step_kernel(StepState* st, AdamScalars* adam, const OptimHyper* hyper, int nopt, unsigned step_mask, int ring) {
+  B200_PDL_PROLOGUE();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   st->n_runs += 1;
   st->info_slot = (st->n_runs - 1) % ring;
@@ -112,6 +114,7 @@ __global__ void prep_step_kernel(StepState* st, AdamScalars* adam, const OptimHy
 // ----------------------------------------------------------------------------- elementwise over blobs
 __global__ void __launch_bounds__(256) adam_blob_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
                                                         const float* __restrict__ g, long long n, const AdamScalars* __restrict__ sc) {
+  B200_PDL_PROLOGUE();
   const AdamScalars s = *sc;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float pi = p[i], mi = m[i], vi = v[i];
@@ -122,12 +125,14 @@ __global__ void __launch_bounds__(256) adam_blob_kernel(float* __restrict__ p, f
 
 // target <- tau*src + target*(1-tau), in the reference's operation order (two roundings + add)
 __global__ void __launch_bounds__(256) polyak_kernel(float* __restrict__ target, const float* __restrict__ src, long long n, float tau, float one_minus_tau) {
+  B200_PDL_PROLOGUE();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     target[i] = __fadd_rn(__fmul_rn(tau, src[i]), __fmul_rn(target[i], one_minus_tau));
   }
 }
 
 __global__ void __launch_bounds__(256) fill_kernel(float* __restrict__ p, long long n, float v) {
+  B200_PDL_PROLOGUE();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
 
@@ -135,6 +140,7 @@ __global__ void __launch_bounds__(256) fill_kernel(float* __restrict__ p, long l
 struct TensorSlice { long long offset; long long numel; };
 __global__ void __launch_bounds__(256) grad_norm_sum_kernel(const float* __restrict__ grad_base, long long grad_gs, const TensorSlice* __restrict__ slices, int nslices,
                                                             float* __restrict__ info, int info_stride, int info_col, long long info_gs, const StepState* st) {
+  B200_PDL_PROLOGUE();
   __shared__ double red[8];
   __shared__ double total;
   const int g = blockIdx.x;
@@ -229,6 +235,7 @@ __global__ void __launch_bounds__(256) td7_encoder_loss_kernel(const float* __re
                                                                float* __restrict__ dzsa, int d_ld, int B, int Z, long long gs_act,
                                                                float* __restrict__ partial, unsigned* __restrict__ counter,
                                                                float* __restrict__ info, int info_stride, int info_col, const StepState* st, long long info_gs) {
+  B200_PDL_PROLOGUE();
   __shared__ float red[32];
   __shared__ bool is_last;
   const int g = blockIdx.y;
@@ -290,6 +297,7 @@ struct CriticLossArgs {
 };
 
 __global__ void __launch_bounds__(1024) critic_loss_kernel(CriticLossArgs a) {
+  B200_PDL_PROLOGUE();
   __shared__ float red[32];
   B200_DYN_SMEM(ScatterTable, scatter_tab);  // hash table for the last-writer-wins scatter
   const int g = blockIdx.x;
@@ -351,6 +359,7 @@ __global__ void __launch_bounds__(1024) critic_loss_kernel(CriticLossArgs a) {
 // actor loss TD7: L = -mean(cat[q1,q2]); the output gradients are the constant -1/(2B)
 __global__ void __launch_bounds__(1024) td7_actor_loss_kernel(const float* __restrict__ q1, const float* __restrict__ q2, int B, long long gs,
                                                               float* __restrict__ info, int info_stride, int info_col, long long info_gs, const StepState* st) {
+  B200_PDL_PROLOGUE();
   __shared__ float red[32];
   const int g = blockIdx.x, b = threadIdx.x;
   float v = (b < B) ? (q1[g * gs + b] + q2[g * gs + b]) : 0.f;
@@ -375,6 +384,7 @@ struct ActorLossArgs {
   int B; long long gs;
 };
 __global__ void __launch_bounds__(1024) minq_actor_loss_kernel(ActorLossArgs a) {
+  B200_PDL_PROLOGUE();
   __shared__ float red[32];
   const int g = blockIdx.x, b = threadIdx.x, B = a.B;
   const long long o = (long long)g * a.gs;
@@ -424,6 +434,7 @@ constexpr float kHalfLog2Pi = 0.9189385332046727f;
 __global__ void __launch_bounds__(256) sac_sample_fwd_kernel(const float* __restrict__ net_out, int ld_out, const float* __restrict__ eps, int ld_eps,
                                                             float* __restrict__ action, int ld_a, float* __restrict__ logp, int B, int A,
                                                             float min_ls, float max_ls, long long gs_out, long long gs_eps, long long gs_a, long long gs_lp) {
+  B200_PDL_PROLOGUE();
   const int g = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
@@ -455,6 +466,7 @@ __global__ void __launch_bounds__(256) sac_sample_bwd_kernel(const float* __rest
                                                             const float* __restrict__ action, int ld_a, const float* __restrict__ da, int ld_da,
                                                             const float* __restrict__ dlogp, float* __restrict__ dout, int ld_dout, int B, int A,
                                                             float min_ls, float max_ls, long long gs_out, long long gs_eps, long long gs_a, long long gs_lp) {
+  B200_PDL_PROLOGUE();
   const int g = blockIdx.y;
   const int row = blockIdx.x * blockDim.y + threadIdx.y;
   if (row >= B) return;

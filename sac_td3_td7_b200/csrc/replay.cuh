@@ -33,6 +33,7 @@ inline int samples_per_warp(int groups) { return groups >= 8 ? 4 : 1; }
 
 __global__ void __launch_bounds__(256) lap_tile_sums_kernel(const float* __restrict__ priority, long long prio_gs, int size,
                                                             double* __restrict__ tile_sums, int ntiles, long long ts_gs) {
+  B200_PDL_PROLOGUE();
   const int g = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x * kPrioTilesPerCta + warp;
@@ -77,6 +78,7 @@ struct SampleArgs {
 
 #define PFX(i) ((i) + ((i) >> 4))
 __global__ void __launch_bounds__(256) lap_sample_kernel(SampleArgs a) {
+  B200_PDL_PROLOGUE();
   B200_DYN_SMEM(double, prefix);  // [ntiles] inclusive tile prefix sums (prioritized mode)
   __shared__ double warp_tot[8];
   const int g = blockIdx.y;
@@ -198,6 +200,7 @@ __global__ void __launch_bounds__(256) lap_sample_kernel(SampleArgs a) {
 __global__ void __launch_bounds__(1024) lap_update_priority_kernel(float* __restrict__ priority, long long prio_gs, float* __restrict__ max_priority,
                                                                    const long long* __restrict__ idx, long long idx_gs, const float* __restrict__ prio,
                                                                    long long p_gs, int B) {
+  B200_PDL_PROLOGUE();
   B200_DYN_SMEM(ScatterTable, tab);
   const int g = blockIdx.x, b = threadIdx.x;
   const float p = (b < B) ? prio[(long long)g * p_gs + b] : 0.f;
@@ -205,6 +208,7 @@ __global__ void __launch_bounds__(1024) lap_update_priority_kernel(float* __rest
 }
 
 __global__ void __launch_bounds__(256) lap_max_kernel(const float* __restrict__ priority, long long prio_gs, int size, float* __restrict__ max_priority) {
+  B200_PDL_PROLOGUE();
   __shared__ float red[32];
   const int g = blockIdx.y;
   const float* p = priority + (long long)g * prio_gs;
@@ -216,6 +220,7 @@ __global__ void __launch_bounds__(256) lap_max_kernel(const float* __restrict__ 
 
 // new rows take the current running max as priority (lap.py:41)
 __global__ void lap_append_priority_kernel(float* __restrict__ priority, const float* __restrict__ max_priority, long long pos, int count, long long cap) {
+  B200_PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) priority[(pos + i) % cap] = *max_priority;
 }
