@@ -129,6 +129,9 @@ int b200rl_agent_set_rng(b200rl_agent* h, uint64_t seed);
 /* fixed device input buffers of the engine ([groups] x {ss[2B][S], action[B][A], reward[B], notdone[B]});
  * group_stride is in floats.  replay.sample can write here directly (zero-copy train_ops). */
 int b200rl_agent_io(b200rl_agent* h, float** ss_dev, float** action_dev, float** reward_dev, float** notdone_dev, int64_t* group_stride);
+/* lap.py:45-64 / simple.py sample(batch) straight into the engine's input buffers (what b200rl_agent_update_n does per
+ * step); the tensors returned by the Python sample() alias these buffers, so train_ops needs no staging copy */
+int b200rl_replay_sample_to_agent(b200rl_replay* h, b200rl_agent* agent, int batch, const float* u_dev, void* stream);
 /* copy a caller batch (five device tensors, rl/utils/annotation.py:23 BATCH) into the input buffers */
 int b200rl_agent_stage_batch(b200rl_agent* h, int group, const float* state_dev, const float* action_dev, const float* reward_dev,
                              const float* next_state_dev, const float* done_dev, void* stream);

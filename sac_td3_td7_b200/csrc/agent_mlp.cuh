@@ -236,6 +236,11 @@ struct MlpAgent : AgentBase {
     }
     GL(Tq[0], M); GL(Tq[1], M); GL(Tq[2], M);
     B200_TRY(launch_critic_loss(M));
+    const bool fix_tree = use_lap && bound != nullptr;  // the write-back changed <= B priorities: repair the sampler's sum tree off the chain
+    if (fix_tree) {
+      B200_TRY(fork.link(M, sP));
+      B200_TRY(bound->fix_sums_last_sample(B, sP));
+    }
     GL(Td[0], M); GL(Td[1], M); GL(Tw, M);
     if (sac) B200_TRY(fork.link(sN, M));
     if (actor) {
@@ -266,6 +271,7 @@ struct MlpAgent : AgentBase {
       B200_TRY(launch_polyak(qt[1], q[1], M));
       if (!sac) B200_TRY(launch_polyak(pol, pol, M));  // target_policy aliases policy (td3.py:86)
     }
+    if (fix_tree) B200_TRY(fork.link(sP, M));
     return kOk;
   }
   int bind_replay(Replay* r) {

@@ -305,6 +305,11 @@ struct TD7Agent : AgentBase {
     B200_TRY(fork.link(sN, M));
     GL(C[10], M); GL(C[11], M); GL(C[12], M);
     B200_TRY(launch_critic_loss(M));
+    const bool fix_tree = use_lap && bound != nullptr;  // the write-back changed <= B priorities: repair the sampler's sum tree off the chain
+    if (fix_tree) {
+      B200_TRY(fork.link(M, sP));
+      B200_TRY(bound->fix_sums_last_sample(B, sP));
+    }
     GL(C[13], M); GL(C[14], M); GL(C[15], M); RL(critic_norm_bwd, M); GL(C[16], M);
     if (actor) {
       B200_TRY(fork.link(sA, M));
@@ -321,6 +326,7 @@ struct TD7Agent : AgentBase {
       GL(Aa[15], M); GL(Aa[16], M); GL(Aa[17], M); GL(Aa[18], M); RL(An[2], M); GL(Aa[19], M);
     }
     B200_TRY(fork.link(sE, M));
+    if (fix_tree) B200_TRY(fork.link(sP, M));
     return kOk;
   }
 

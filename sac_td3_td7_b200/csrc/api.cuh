@@ -147,6 +147,7 @@ int b200rl_replay_get_state(b200rl_replay* h, int group, int64_t* ptr, int64_t* 
   return kOk;
 }
 int b200rl_replay_set_cursor(b200rl_replay* h, int group, int64_t ptr, int64_t size) {
+  if (h) h->r.sums_valid = false;
   B200_REQUIRE(h && group >= 0 && group < h->r.groups, "bad handle or group");
   B200_REQUIRE(ptr >= 0 && ptr < h->r.capacity && size >= 0 && size <= h->r.capacity, "cursor out of range");
   h->r.ptr[group] = ptr;
@@ -173,6 +174,7 @@ int b200rl_replay_write_priority(b200rl_replay* h, int group, int64_t first, int
   if (count > 0)
     B200_CHECK_CUDA(cudaMemcpyAsync(h->r.d_priority + (long long)group * h->r.cap_pad + first, in_host, (size_t)count * sizeof(float), cudaMemcpyHostToDevice,
                                     as_stream(stream)));
+  h->r.sums_valid = false;  // the next sample rebuilds the sum tree
   if (max_priority >= 0.f)
     B200_CHECK_CUDA(cudaMemcpyAsync(h->r.d_max_priority + group, &max_priority, sizeof(float), cudaMemcpyHostToDevice, as_stream(stream)));
   B200_CHECK_CUDA(cudaStreamSynchronize(as_stream(stream)));
@@ -424,6 +426,13 @@ int b200rl_agent_io(b200rl_agent* h, float** ss_dev, float** action_dev, float**
   if (group_stride) *group_stride = a.act_stride;
   return kOk;
 }
+int b200rl_replay_sample_to_agent(b200rl_replay* replay, b200rl_agent* h, int batch, const float* u_dev, void* stream) {
+  B200_REQUIRE(h && replay, "null argument");
+  AgentBase& a = *h->base;
+  B200_REQUIRE(replay->r.groups == a.G && replay->r.S == a.S && replay->r.A == a.A, "replay buffer and agent shapes differ");
+  B200_REQUIRE(batch == a.B, "sample_to_agent: the batch size must be the engine's");
+  return replay->r.sample(batch, u_dev, a.replay_outputs(), as_stream(stream));
+}
 int b200rl_agent_stage_batch(b200rl_agent* h, int group, const float* state_dev, const float* action_dev, const float* reward_dev, const float* next_state_dev,
                              const float* done_dev, void* stream) {
   B200_REQUIRE(h && state_dev && action_dev && reward_dev && next_state_dev && done_dev, "null argument");
@@ -630,9 +639,8 @@ int b200rl_replay_time_sample(b200rl_replay* h, int batch, int warmup, int iters
   for (int i = 0; i < iters; ++i) B200_TRY(r.sample(batch, nullptr, o, s));
   B200_CHECK_CUDA(cudaEventRecord(e1, s));
   B200_CHECK_CUDA(cudaEventSynchronize(e1));
-  float both = 0.f;
-  B200_CHECK_CUDA(cudaEventElapsedTime(&both, e0, e1));
-  ms_out2[1] = both / (float)iters - ms_out2[0];
+  B200_CHECK_CUDA(cudaEventElapsedTime(&ms_out2[1], e0, e1));
+  ms_out2[1] /= (float)iters;
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
 #else

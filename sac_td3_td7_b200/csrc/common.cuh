@@ -87,14 +87,24 @@ inline void launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size
     ++b200rl::launch_counter();                                                          \
     b200rl::launch_ex(kernel, dim3(grid), dim3(block), (smem), (stream), __VA_ARGS__);   \
   } while (0)
-#define B200_PDL_PROLOGUE()                                   \
-  do {                                                        \
-    asm volatile("griddepcontrol.wait;" ::: "memory");        \
-    asm volatile("griddepcontrol.launch_dependents;" ::);     \
+// Programmatic dependent launch: TRIGGER lets the next kernel of the stream be scheduled (its CTAs run their
+// parameter-only setup and then block in WAIT); WAIT returns once every prerequisite grid has completed and its
+// memory is visible.  No-ops unless the launch carried the attribute (B200RL_PDL=1).
+#define B200_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define B200_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::)
+#define B200_PDL_PROLOGUE() \
+  do {                      \
+    B200_PDL_WAIT();        \
+    B200_PDL_TRIGGER();     \
   } while (0)
 #endif
 #ifdef B200_EMU
 #define B200_PDL_PROLOGUE() do { } while (0)
+#define B200_PDL_WAIT() do { } while (0)
+#define B200_PDL_TRIGGER() do { } while (0)
+#define B200_NOINLINE __attribute__((noinline))
+#else
+#define B200_NOINLINE __noinline__
 #endif
 
 namespace b200rl {

@@ -180,6 +180,49 @@ __device__ __forceinline__ void cp_async_wait() {
 #endif
 }
 
+// copy one thread's two strips of the chunk starting at reduction offset r0 (segment length rlen), zero-filling
+// whatever lies outside the operand
+template <bool KMAJOR>
+B200_NOINLINE __device__ void stage_ragged(float* tile, const float* src, int delta, int dst, int pos, int row, bool ok0, bool ok1, bool vec, int r0, int rlen,
+                                           int cmax) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float* q = src + (h ? delta : 0);
+    if (KMAJOR) {
+      float* d = tile + (h ? ((dst ^ 16) + 16 * kBK) : dst);
+      const int p = r0 + pos;
+      const bool ok = h ? ok1 : ok0;
+      if (vec && ok && p + 3 < rlen) {
+        cp_async16(d, q);
+      } else {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && p < rlen) {
+          v.x = q[0];
+          if (p + 1 < rlen) v.y = q[1];
+          if (p + 2 < rlen) v.z = q[2];
+          if (p + 3 < rlen) v.w = q[3];
+        }
+        *reinterpret_cast<float4*>(d) = v;
+      }
+    } else {
+      float* d = tile + dst + h * (32 * kTile);
+      const bool in = (r0 + row + 32 * h) < rlen;
+      if (vec && in) {
+        cp_async16(d, q);
+      } else {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (in && ok0) {
+          v.x = q[0];
+          if (pos + 1 < cmax) v.y = q[1];
+          if (pos + 2 < cmax) v.z = q[2];
+          if (pos + 3 < cmax) v.w = q[3];
+        }
+        *reinterpret_cast<float4*>(d) = v;
+      }
+    }
+  }
+}
+
 // One operand of one reduction segment, as seen by one thread: the two 16-byte strips it copies per
 // chunk.  Shared-memory tile layouts (32 output indices x 64 reduction indices):
 //   K-major (operand contiguous along the reduction r in global): row = c, 16 float4 slots along r,
@@ -198,6 +241,7 @@ struct OperandCursor {
   int row;           // C-major: r offset of strip 0 inside the chunk (strip 1: + 32)
   bool ok0, ok1;     // K-major: output row of strip 0 / 1 inside the problem; C-major: strip has >= 1 valid column
   bool vec;          // 16-byte aligned source (and, C-major, a complete strip): cp.async path
+  bool all;          // both strips of a chunk that lies fully inside the segment take the cp.async path
 
   __device__ __forceinline__ void init(const float* base, int ld, int c0, int cmax, int tid, int r_start) {
     if (KMAJOR) {
@@ -210,6 +254,7 @@ struct OperandCursor {
       src = base + (long long)(c0 + c) * ld + (pos + r_start);
       delta = 16 * ld;
       vec = aligned16(src);  // 16*ld floats and the 64-float bump keep the alignment
+      all = vec && ok0 && ok1;
     } else {
       const int r = tid >> 3, s = tid & 7;
       dst = r * kTile + (s << 2);
@@ -219,46 +264,24 @@ struct OperandCursor {
       src = base + (long long)(r_start + r) * ld + pos;
       delta = 32 * ld;
       vec = (pos + 3 < cmax) && aligned16(src);
+      all = vec;
     }
   }
-  // copy this thread's strips of the chunk starting at reduction offset r0 (segment length rlen)
-  __device__ __forceinline__ void stage(float* tile, int r0, int rlen, int cmax) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const float* q = src + (h ? delta : 0);
-      if (KMAJOR) {
-        float* d = tile + (h ? ((dst ^ 16) + 16 * kBK) : dst);
-        const int p = r0 + pos;
-        const bool ok = h ? ok1 : ok0;
-        if (vec && ok && p + 3 < rlen) {
-          cp_async16(d, q);
-        } else {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok && p < rlen) {
-            v.x = q[0];
-            if (p + 1 < rlen) v.y = q[1];
-            if (p + 2 < rlen) v.z = q[2];
-            if (p + 3 < rlen) v.w = q[3];
-          }
-          *reinterpret_cast<float4*>(d) = v;
-        }
-      } else {
-        float* d = tile + dst + h * (32 * kTile);
-        const bool in = (r0 + row + 32 * h) < rlen;
-        if (vec && in) {
-          cp_async16(d, q);
-        } else {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (in && ok0) {
-            v.x = q[0];
-            if (pos + 1 < cmax) v.y = q[1];
-            if (pos + 2 < cmax) v.z = q[2];
-            if (pos + 3 < cmax) v.w = q[3];
-          }
-          *reinterpret_cast<float4*>(d) = v;
-        }
-      }
+  // fast path: the whole chunk lies inside the segment and both strips are complete and aligned
+  __device__ __forceinline__ void stage_full(float* tile) {
+    if (KMAJOR) {
+      cp_async16(tile + dst, src);
+      cp_async16(tile + ((dst ^ 16) + 16 * kBK), src + delta);
+      src += kBK;
+    } else {
+      cp_async16(tile + dst, src);
+      cp_async16(tile + dst + 32 * kTile, src + delta);
+      src += 2ll * delta;
     }
+  }
+  // general path (ragged widths such as 17 / 6 / 23, segment tails, unaligned rows): out of line, it is rare
+  __device__ __forceinline__ void stage(float* tile, int r0, int rlen, int cmax) {
+    stage_ragged<KMAJOR>(tile, src, delta, dst, pos, row, ok0, ok1, vec, r0, rlen, cmax);
     src += KMAJOR ? (long long)kBK : 2ll * delta;
   }
 };
@@ -349,9 +372,11 @@ __device__ __forceinline__ void store_quad(float* p, const float (&o)[4], int nv
   }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_constant__ FfmaLaunch L) {
-  B200_PDL_PROLOGUE();
+// MINB = CTAs per SM the register budget is sized for: 2 (<= 128 registers) for launches of more than one CTA
+// per SM, 1 (no cap: addresses and fragments stay in registers) for the small launches of a single agent.
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(kGemmThreads, MINB) gemm_kernel(const __grid_constant__ FfmaLaunch L) {
+  B200_PDL_TRIGGER();  // the setup below reads kernel parameters only: it may overlap the previous kernel
   B200_PROBE_DECL
   constexpr bool A_KM = (MODE != kWgrad);  // A contiguous along the reduction in global memory
   constexpr bool B_KM = (MODE == kFwd);
@@ -410,8 +435,11 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_cons
   auto issue = [&](int stage) {
     float* At = smem + stage * kStageElems;
     float* Bt = At + kTile * kBK;
-    ca.stage(At, pr0, plen, I);
+    const bool full = pr0 + kBK <= plen;
+    if (full && ca.all) ca.stage_full(At);
+    else ca.stage(At, pr0, plen, I);
     if (ones) stage_ones(Bt, j0, pr0, plen, tid);
+    else if (full && cb.all) cb.stage_full(Bt);
     else cb.stage(Bt, pr0, plen, J);
     pr0 += kBK;
     if (pr0 >= plen && ++pseg < sp.nseg) open_segment(0);
@@ -427,6 +455,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_cons
     open_segment(skip * kBK);
   }
   B200_PROBE(2)
+  B200_PDL_WAIT();  // operands written by earlier kernels are read from here on
 
   // prologue: fill kStages-1 stages
 #pragma unroll
@@ -436,15 +465,38 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_cons
   }
   B200_PROBE(3)
 
+  // loop-invariant shared-memory read offsets of this thread (floats, relative to a stage's A / B tile)
+  int a_off[4], b_off[8];
+  if (A_KM) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) a_off[a] = (li * 4 + a) * kBK + (((2 * warp) ^ li) << 2);  // h = 1: ^ 4
+  } else {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) a_off[a] = (warp * 8 + a) * kTile + li * 4;  // rr = a; h = 1: + 4 * kTile
+  }
+  if (B_KM) {
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int col = lj * 8 + b;
+      b_off[b] = col * kBK + (((2 * warp) ^ ((col >> 2) & 7)) << 2);  // h = 1: ^ 4
+    }
+  } else {
+#pragma unroll
+    for (int b = 0; b < 8; ++b) b_off[b] = (warp * 8 + (b >> 1)) * kTile + lj * 8 + 4 * (b & 1);  // rr = b >> 1, half-row b & 1
+  }
+
+  int rs = 0, ws = kStages - 1;  // stage read by chunk c / stage refilled during chunk c
   for (int c = 0; c < nchunks; ++c) {
     cp_async_wait<kStages - 2>();  // chunk c has landed (this thread's copies)
     __syncthreads();               // ... and everybody's; also: the stage refilled below is no longer being read
     if (c == 0) { B200_PROBE(4) }
-    if (c + kStages - 1 < nchunks) issue((c + kStages - 1) % kStages);
+    if (c + kStages - 1 < nchunks) issue(ws);
     cp_async_commit();
 
-    const float* As = smem + (c % kStages) * kStageElems;
+    const float* As = smem + rs * kStageElems;
     const float* Bs = As + kTile * kBK;
+    rs = (rs + 1 == kStages) ? 0 : rs + 1;
+    ws = (ws + 1 == kStages) ? 0 : ws + 1;
     // this warp's 8 reduction indices of the chunk: r = 8*warp .. 8*warp+7, in two halves of 4
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -452,28 +504,27 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_cons
       if (A_KM) {
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-          const float4 v = *reinterpret_cast<const float4*>(&As[(li * 4 + a) * kBK + (((2 * warp + h) ^ li) << 2)]);
+          const float4 v = *reinterpret_cast<const float4*>(&As[a_off[a] ^ (h << 2)]);
           av[a][0] = v.x; av[a][1] = v.y; av[a][2] = v.z; av[a][3] = v.w;
         }
       } else {
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
-          const float4 v = *reinterpret_cast<const float4*>(&As[(warp * 8 + h * 4 + rr) * kTile + li * 4]);
+          const float4 v = *reinterpret_cast<const float4*>(&As[a_off[rr] + h * 4 * kTile]);
           av[0][rr] = v.x; av[1][rr] = v.y; av[2][rr] = v.z; av[3][rr] = v.w;
         }
       }
       if (B_KM) {
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
-          const int col = lj * 8 + b;
-          const float4 v = *reinterpret_cast<const float4*>(&Bs[col * kBK + (((2 * warp + h) ^ ((col >> 2) & 7)) << 2)]);
+          const float4 v = *reinterpret_cast<const float4*>(&Bs[b_off[b] ^ (h << 2)]);
           bv[b][0] = v.x; bv[b][1] = v.y; bv[b][2] = v.z; bv[b][3] = v.w;
         }
       } else {
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
-          const float4 v0 = *reinterpret_cast<const float4*>(&Bs[(warp * 8 + h * 4 + rr) * kTile + lj * 8]);
-          const float4 v1 = *reinterpret_cast<const float4*>(&Bs[(warp * 8 + h * 4 + rr) * kTile + lj * 8 + 4]);
+          const float4 v0 = *reinterpret_cast<const float4*>(&Bs[b_off[2 * rr] + h * 4 * kTile]);
+          const float4 v1 = *reinterpret_cast<const float4*>(&Bs[b_off[2 * rr + 1] + h * 4 * kTile]);
           bv[0][rr] = v0.x; bv[1][rr] = v0.y; bv[2][rr] = v0.z; bv[3][rr] = v0.w;
           bv[4][rr] = v1.x; bv[5][rr] = v1.y; bv[6][rr] = v1.z; bv[7][rr] = v1.w;
         }

@@ -11,25 +11,57 @@
 // (fp32 storage is value-identical to the reference's fp64-store + fp32-cast).
 // priority: fp32[capacity] (+pad) per stacked seed; max_priority: one fp32 per seed, on device.
 //
-// Sampling is reduce-then-search, never materialising the 1M-entry prefix array:
-//   1. lap_tile_sums_kernel: fp64 sum of every 256-priority tile  (reads 4*size bytes)
-//   2. lap_sample_kernel:    each CTA scans the tile sums in shared memory (fp64), each warp
-//      takes one draw: binary search over tile prefixes (compared after rounding to fp32,
-//      exactly like the reference's fp32 prefix array), warp-shuffle scan inside the tile,
-//      then the warp copies the chosen row out with 128-bit loads.
+// Sampling never materialises the 1M-entry prefix array.  A three-level sum tree is kept in HBM:
+//     priority[cap]  ->  tile_sums[cap/256] (fp64)  ->  super_sums[cap/16384] (fp64)
+// and every kernel that writes priorities (append, the LAP write-back inside the critic-loss
+// kernel, update_priority) repairs the <= B touched tiles and their super-tiles right away
+// (lap_fix_sums_kernel / the tail of lap_append_priority_kernel), so a draw costs no pass over
+// the priorities at all:
+//   lap_sample_kernel: one warp per draw walks the tree top-down -- warp scan of the super sums,
+//   of the 64 tile sums of the chosen super-tile, of the 256 priorities of the chosen tile; every
+//   comparison is made on the fp64 prefix rounded to fp32, exactly like the reference's fp32
+//   prefix array -- then copies the chosen row out with 128-bit loads.
+//   lap_tile_sums_kernel + lap_super_sums_kernel rebuild the tree from scratch (bulk loads,
+//   restored checkpoints).
 // Priorities are fp32 values >= 1 (or 0), so fp64 partial sums are EXACT for any summation
 // order while max_priority * size < 2^30; the sampled indices are then bit-identical to
-// torch.cumsum + torch.searchsorted on the CPU.
+// torch.cumsum + torch.searchsorted on the CPU, and an incrementally repaired tree is
+// bit-identical to a rebuilt one.
 #pragma once
 #include "host.cuh"
 
 namespace b200rl {
 
 constexpr int kPrioTile = 256;       // priorities per tile (one warp: 32 lanes x 8)
-constexpr int kPrioTilesPerCta = 8;  // 2048 priorities per CTA in the reduce kernel
-// draws handled by one warp of the search/gather kernel: 1 for a single agent (latency), 4 when many seeds
-// are stacked (fewer CTAs re-scan the tile sums)
-inline int samples_per_warp(int groups) { return groups >= 8 ? 4 : 1; }
+constexpr int kPrioTilesPerCta = 8;  // 2048 priorities per CTA in the rebuild kernel
+constexpr int kSuperTiles = 64;      // tiles per super-tile (one warp: 32 lanes x 2)
+
+__device__ __forceinline__ float4 ld_cg4(const float* p) {
+#ifdef B200_EMU
+  return *reinterpret_cast<const float4*>(p);
+#else
+  return __ldcg(reinterpret_cast<const float4*>(p));
+#endif
+}
+__device__ __forceinline__ double ld_cgd(const double* p) {
+#ifdef B200_EMU
+  return *p;
+#else
+  return __ldcg(p);
+#endif
+}
+__device__ __forceinline__ double shfl_double(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// exact fp64 sum of one whole tile (entries past `size` are zero by construction), by one warp
+__device__ __forceinline__ double tile_sum_warp(const float* tile_base, int lane) {
+  const float4 a = ld_cg4(tile_base + lane * 4);
+  const float4 b = ld_cg4(tile_base + 128 + lane * 4);
+  const double s = ((double)a.x + (double)a.y) + ((double)a.z + (double)a.w) + (((double)b.x + (double)b.y) + ((double)b.z + (double)b.w));
+  return warp_sum(s);
+}
+__device__ __forceinline__ double super_sum_warp(const double* first_tile, int lane) {
+  return warp_sum(ld_cgd(first_tile + lane) + ld_cgd(first_tile + 32 + lane));
+}
 
 __global__ void __launch_bounds__(256) lap_tile_sums_kernel(const float* __restrict__ priority, long long prio_gs, int size,
                                                             double* __restrict__ tile_sums, int ntiles, long long ts_gs) {
@@ -57,9 +89,78 @@ __global__ void __launch_bounds__(256) lap_tile_sums_kernel(const float* __restr
   if (lane == 0) tile_sums[(long long)g * ts_gs + tile] = s;
 }
 
+__global__ void __launch_bounds__(256) lap_super_sums_kernel(const double* __restrict__ tile_sums, long long ts_gs, double* __restrict__ super_sums, long long ss_gs,
+                                                             int nsuper) {
+  B200_PDL_PROLOGUE();
+  const int g = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sup = blockIdx.x * 8 + warp;
+  if (sup >= nsuper) return;
+  const double s = super_sum_warp(tile_sums + (long long)g * ts_gs + (long long)sup * kSuperTiles, lane);
+  if (lane == 0) super_sums[(long long)g * ss_gs + sup] = s;
+}
+
+// Repair the sum tree after up to `n` priorities changed.  One CTA per stacked seed: phase 1 recomputes the
+// tile of every touched entry (duplicates rewrite the same value), phase 2 the super-tile of every touched
+// entry from the repaired tile sums.  Entries: idx[i] when idx != null, else (pos + i) % cap.
+struct FixArgs {
+  const float* priority; long long prio_gs;
+  double* tile_sums; long long ts_gs;
+  double* super_sums; long long ss_gs;
+  const long long* idx; long long idx_gs;
+  long long pos, cap;
+  int n;
+};
+__device__ __forceinline__ void lap_fix_block(const FixArgs& a, int g) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const float* prio = a.priority + (long long)g * a.prio_gs;
+  double* ts = a.tile_sums + (long long)g * a.ts_gs;
+  double* ss = a.super_sums + (long long)g * a.ss_gs;
+  const long long* idx = a.idx ? a.idx + (long long)g * a.idx_gs : nullptr;
+  if (idx) {
+    for (int i = warp; i < a.n; i += nw) {
+      const long long tile = idx[i] / kPrioTile;
+      const double s = tile_sum_warp(prio + tile * kPrioTile, lane);
+      if (lane == 0) ts[tile] = s;
+    }
+  } else {  // a contiguous (possibly wrapping) range: visit every covered tile once
+    for (int part = 0; part < 2; ++part) {
+      const long long lo = part == 0 ? a.pos : 0, hi = part == 0 ? (a.pos + a.n < a.cap ? a.pos + a.n : a.cap) : a.pos + a.n - a.cap;  // [lo, hi)
+      if (hi <= lo) continue;
+      for (long long tile = lo / kPrioTile + warp; tile <= (hi - 1) / kPrioTile; tile += nw) {
+        const double s = tile_sum_warp(prio + tile * kPrioTile, lane);
+        if (lane == 0) ts[tile] = s;
+      }
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+  if (idx) {
+    for (int i = warp; i < a.n; i += nw) {
+      const long long sup = idx[i] / (kPrioTile * kSuperTiles);
+      const double s = super_sum_warp(ts + sup * kSuperTiles, lane);
+      if (lane == 0) ss[sup] = s;
+    }
+  } else {
+    for (int part = 0; part < 2; ++part) {
+      const long long lo = part == 0 ? a.pos : 0, hi = part == 0 ? (a.pos + a.n < a.cap ? a.pos + a.n : a.cap) : a.pos + a.n - a.cap;
+      if (hi <= lo) continue;
+      for (long long sup = lo / (kPrioTile * kSuperTiles) + warp; sup <= (hi - 1) / (kPrioTile * kSuperTiles); sup += nw) {
+        const double s = super_sum_warp(ts + sup * kSuperTiles, lane);
+        if (lane == 0) ss[sup] = s;
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(1024) lap_fix_sums_kernel(FixArgs a) {
+  B200_PDL_PROLOGUE();
+  lap_fix_block(a, blockIdx.x);
+}
+
 struct SampleArgs {
   const float* priority; long long prio_gs;
   const double* tile_sums; long long ts_gs; int ntiles;
+  const double* super_sums; long long ss_gs; int nsuper;
   int size;
   const float* u; long long u_gs;          // injected uniforms [B] (null -> Philox)
   unsigned long long seed, counter;        // Philox stream when u == null
@@ -73,42 +174,47 @@ struct SampleArgs {
   float* done; long long done_gs;
   int B;
   int prioritized;
-  int spw;  // samples per warp
 };
 
-#define PFX(i) ((i) + ((i) >> 4))
+// K consecutive values per lane (lane l holds elements l*K .. l*K+K-1 of a 32*K run whose exclusive prefix
+// is `base`): position of the first element whose fp32-rounded inclusive prefix reaches v (-1: none), and
+// the exact exclusive prefix of that element.
+template <int K>
+__device__ __forceinline__ int warp_first_reaching(const double (&x)[K], double base, float v, int lane, double* excl_out) {
+  double c[K];
+  double run = 0.0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    run += x[k];
+    c[k] = run;
+  }
+  const double incl = warp_inclusive_scan(run, lane);
+  const double excl = base + (incl - run);
+  int kfirst = K;
+#pragma unroll
+  for (int k = K - 1; k >= 0; --k)
+    if ((float)(excl + c[k]) >= v) kfirst = k;
+  const unsigned hit = __ballot_sync(0xffffffffu, kfirst < K);
+  double before = excl;
+#pragma unroll
+  for (int k = 1; k < K; ++k)
+    if (kfirst == k) before = excl + c[k - 1];
+  if (hit == 0u) {
+    *excl_out = base;
+    return -1;
+  }
+  const int src = __ffs((int)hit) - 1;
+  const int kk = __shfl_sync(0xffffffffu, kfirst, src);
+  *excl_out = shfl_double(before, src);
+  return src * K + kk;
+}
+
 __global__ void __launch_bounds__(256) lap_sample_kernel(SampleArgs a) {
   B200_PDL_PROLOGUE();
-  B200_DYN_SMEM(double, prefix);  // [ntiles] inclusive tile prefix sums (prioritized mode)
-  __shared__ double warp_tot[8];
   const int g = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int size = a.size;
-
-  if (a.prioritized) {
-    // inclusive scan of the tile sums in shared memory: coalesced copy in, per-thread serial scan of
-    // a contiguous run, warp/block scan of the run totals, add the offsets back
-    const int nt = a.ntiles;
-    const double* ts = a.tile_sums + (long long)g * a.ts_gs;
-    // (element i lives at PFX(i) = i + i/16: one pad slot per 16 keeps the per-thread runs off a single bank)
-    for (int t = tid; t < nt; t += 256) prefix[PFX(t)] = ts[t];
-    __syncthreads();
-    const int per = (nt + 255) / 256;
-    const int lo = min(tid * per, nt), hi = min(lo + per, nt);
-    double local = 0.0;
-    for (int t = lo; t < hi; ++t) { local += prefix[PFX(t)]; prefix[PFX(t)] = local; }
-    const double incl = warp_inclusive_scan(local, lane);
-    if (lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    double off = incl - local;
-    for (int w = 0; w < warp; ++w) off += warp_tot[w];
-    for (int t = lo; t < hi; ++t) prefix[PFX(t)] += off;
-    __syncthreads();
-  }
-
-  // each warp takes kSamplesPerWarp draws in turn (fewer CTAs re-scan the tile sums)
-  for (int sw = 0; sw < a.spw; ++sw) {
-  const int b = (blockIdx.x * 8 + warp) * a.spw + sw;
+  const int b = blockIdx.x * 8 + warp;
   if (b >= a.B) return;
 
   float u;
@@ -124,43 +230,48 @@ __global__ void __launch_bounds__(256) lap_sample_kernel(SampleArgs a) {
 
   long long idx;
   if (a.prioritized) {
-    const int nt = a.ntiles;
-    const float total32 = (float)prefix[PFX(nt - 1)];
-    const float v = __fmul_rn(u, total32);
-    // first tile whose fp32-rounded inclusive prefix reaches v
-    int lo = 0, hi = nt - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if ((float)prefix[PFX(mid)] >= v) hi = mid; else lo = mid + 1;
-    }
-    const int tile = lo;
-    const double base = tile > 0 ? prefix[PFX(tile - 1)] : 0.0;
-    const float* p = a.priority + (long long)g * a.prio_gs + (long long)tile * kPrioTile + lane * 8;
-    const float4 x0 = *reinterpret_cast<const float4*>(p);
-    const float4 x1 = *reinterpret_cast<const float4*>(p + 4);
-    const int e0 = tile * kPrioTile + lane * 8;
-    float pv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-    double c[8];
+    // ---- level 0: super-tiles.  Lane l owns the contiguous run [l*per, l*per+per) of super sums.
+    const double* ss = a.super_sums + (long long)g * a.ss_gs;
+    const int nsup = a.nsuper;
+    const int per = (nsup + 31) >> 5;
+    const int s_lo = min(lane * per, nsup), s_hi = min(s_lo + per, nsup);
     double run = 0.0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (e0 + k < size) run += (double)pv[k];
-      c[k] = run;
-    }
+    for (int t = s_lo; t < s_hi; ++t) run += ld_cgd(ss + t);
     const double incl = warp_inclusive_scan(run, lane);
-    const double excl = base + (incl - run);
-    int kfirst = 8;
-#pragma unroll
-    for (int k = 7; k >= 0; --k)
-      if (e0 + k < size && (float)(excl + c[k]) >= v) kfirst = k;
-    const unsigned hit = __ballot_sync(0xffffffffu, kfirst < 8);
-    if (hit == 0u) {
-      idx = size - 1;  // unreachable for u < 1; keeps the gather in range
-    } else {
-      const int src = __ffs((int)hit) - 1;
-      const int kk = __shfl_sync(0xffffffffu, kfirst, src);
-      idx = (long long)tile * kPrioTile + src * 8 + kk;
+    const double total = shfl_double(incl, 31);
+    const float v = __fmul_rn(u, (float)total);
+    double acc = incl - run;  // exclusive prefix of this lane's run
+    int sfirst = -1;
+    double sbase = 0.0;
+    for (int t = s_lo; t < s_hi; ++t) {
+      const double nx = acc + ld_cgd(ss + t);
+      if (sfirst < 0 && (float)nx >= v) { sfirst = t; sbase = acc; }
+      acc = nx;
     }
+    const unsigned shit = __ballot_sync(0xffffffffu, sfirst >= 0);
+    int sup = nsup - 1;
+    double base = 0.0;
+    if (shit != 0u) {
+      const int src = __ffs((int)shit) - 1;
+      sup = __shfl_sync(0xffffffffu, sfirst, src);
+      base = shfl_double(sbase, src);
+    }
+    // ---- level 1: the 64 tiles of that super-tile
+    const double* ts = a.tile_sums + (long long)g * a.ts_gs + (long long)sup * kSuperTiles;
+    const double t2[2] = {ld_cgd(ts + 2 * lane), ld_cgd(ts + 2 * lane + 1)};
+    double tbase;
+    int tin = warp_first_reaching<2>(t2, base, v, lane, &tbase);
+    if (tin < 0) { tin = min(kSuperTiles - 1, a.ntiles - 1 - sup * kSuperTiles); tbase = base; }
+    const int tile = sup * kSuperTiles + tin;
+    // ---- level 2: the 256 priorities of that tile
+    const float* p = a.priority + (long long)g * a.prio_gs + (long long)tile * kPrioTile + lane * 8;
+    const float4 x0 = ld_cg4(p);
+    const float4 x1 = ld_cg4(p + 4);
+    const double pv[8] = {(double)x0.x, (double)x0.y, (double)x0.z, (double)x0.w, (double)x1.x, (double)x1.y, (double)x1.z, (double)x1.w};
+    double ebase;
+    const int ein = warp_first_reaching<8>(pv, tbase, v, lane, &ebase);
+    idx = ein >= 0 ? (long long)tile * kPrioTile + ein : (long long)size - 1;
+    if (idx > size - 1) idx = size - 1;  // unreachable for u < 1; keeps the gather in range
   } else {
     // uniform: prefix is (float)(i+1); first i with (float)(i+1) >= u * (float)size
     const float v = __fmul_rn(u, (float)size);
@@ -194,17 +305,19 @@ __global__ void __launch_bounds__(256) lap_sample_kernel(SampleArgs a) {
       else if (pos < o_end) ns[pos - o_next] = val;
     }
   }
-  }  // samples of this warp
 }
 
 __global__ void __launch_bounds__(1024) lap_update_priority_kernel(float* __restrict__ priority, long long prio_gs, float* __restrict__ max_priority,
                                                                    const long long* __restrict__ idx, long long idx_gs, const float* __restrict__ prio,
-                                                                   long long p_gs, int B) {
+                                                                   long long p_gs, int B, FixArgs fix) {
   B200_PDL_PROLOGUE();
   B200_DYN_SMEM(ScatterTable, tab);
   const int g = blockIdx.x, b = threadIdx.x;
   const float p = (b < B) ? prio[(long long)g * p_gs + b] : 0.f;
   lap_scatter_block(priority + (long long)g * prio_gs, max_priority + g, idx + (long long)g * idx_gs, p, b, B, tab);
+  __threadfence_block();
+  __syncthreads();
+  lap_fix_block(fix, g);
 }
 
 __global__ void __launch_bounds__(256) lap_max_kernel(const float* __restrict__ priority, long long prio_gs, int size, float* __restrict__ max_priority) {
@@ -224,6 +337,15 @@ __global__ void lap_append_priority_kernel(float* __restrict__ priority, const f
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) priority[(pos + i) % cap] = *max_priority;
 }
+// the per-environment-step form (a handful of rows): one CTA writes the priorities and repairs the sum tree
+__global__ void __launch_bounds__(1024) lap_append_fix_kernel(float* __restrict__ priority, const float* __restrict__ max_priority, FixArgs fix) {
+  B200_PDL_PROLOGUE();
+  const float m = *max_priority;
+  for (int i = threadIdx.x; i < fix.n; i += blockDim.x) priority[(fix.pos + i) % fix.cap] = m;
+  __threadfence_block();
+  __syncthreads();
+  lap_fix_block(fix, 0);
+}
 
 // ----------------------------------------------------------------------------- host object
 struct Replay {
@@ -236,6 +358,9 @@ struct Replay {
   float* d_priority = nullptr;
   float* d_max_priority = nullptr;
   double* d_tile_sums = nullptr;
+  double* d_super_sums = nullptr;
+  int max_supers = 0;
+  bool sums_valid = false;  // the sum tree matches the priorities (false after bulk writes: rebuilt by the next sample)
   long long* d_idx = nullptr;  // last sampled indices [groups][max_batch]
   float* d_prio_stage = nullptr;
   int max_batch = 4096;
@@ -253,8 +378,8 @@ struct Replay {
     capacity = cap; S = s; A = a; groups = g; prioritized = prio; share_rows = share;
     row_stride = (int)round_up(2 * S + A + 2, 4);
     cap_pad = round_up(capacity, kPrioTile * kPrioTilesPerCta);
-    max_tiles = (int)(cap_pad / kPrioTile);
-    B200_REQUIRE((size_t)(max_tiles + max_tiles / 16 + 1) * sizeof(double) <= 200 * 1024, "replay: capacity too large for the shared-memory tile scan (max ~26M rows)");
+    max_tiles = (int)round_up(cap_pad / kPrioTile, kSuperTiles);
+    max_supers = max_tiles / kSuperTiles;
     const long long row_sets = share_rows ? 1 : groups;
     B200_TRY(arena.alloc(&d_rows, (size_t)row_sets * capacity * row_stride));
     B200_TRY(arena.alloc(&d_idx, (size_t)groups * max_batch));
@@ -263,14 +388,13 @@ struct Replay {
     if (prioritized) {
       B200_TRY(arena.alloc(&d_priority, (size_t)groups * cap_pad));
       B200_TRY(arena.alloc(&d_tile_sums, (size_t)groups * max_tiles));
+      B200_TRY(arena.alloc(&d_super_sums, (size_t)groups * max_supers));
+      sums_valid = true;  // all zero
     }
     std::vector<float> ones(groups, 1.0f);  // lap.py:29 max_priority = 1
     B200_CHECK_CUDA(cudaMemcpy(d_max_priority, ones.data(), groups * sizeof(float), cudaMemcpyHostToDevice));
     ptr.assign(groups, 0);
     size.assign(groups, 0);
-#ifndef B200_EMU
-    B200_CHECK_CUDA(cudaFuncSetAttribute(lap_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-#endif
     return kOk;
   }
 
@@ -288,12 +412,58 @@ struct Replay {
         B200_CHECK_CUDA(cudaMemcpyAsync(dst_base, rows + first * row_stride, (size_t)(count - first) * row_stride * sizeof(float), kind, stream));
     }
     if (prioritized) {
-      dim3 grid((unsigned)ceil_div((int)count, 256)), block(256);
-      B200_LAUNCH(lap_append_priority_kernel, grid, block, 0, stream, d_priority + (long long)g * cap_pad, d_max_priority + g, pos, (int)count, capacity);
+      if (count <= 4096 && sums_valid) {
+        FixArgs f = fix_args(nullptr, 0, (int)count);
+        f.priority += (long long)g * cap_pad; f.tile_sums += (long long)g * max_tiles; f.super_sums += (long long)g * max_supers;
+        f.pos = pos;
+        B200_LAUNCH(lap_append_fix_kernel, dim3(1), dim3(count <= 32 ? 64 : 1024), 0, stream, d_priority + (long long)g * cap_pad, d_max_priority + g, f);
+      } else {
+        dim3 grid((unsigned)ceil_div((int)count, 256)), block(256);
+        B200_LAUNCH(lap_append_priority_kernel, grid, block, 0, stream, d_priority + (long long)g * cap_pad, d_max_priority + g, pos, (int)count, capacity);
+        sums_valid = false;
+      }
       B200_CHECK_LAUNCH();
     }
     ptr[g] = (pos + count) % capacity;
     size[g] = std::min(size[g] + count, capacity);
+    return kOk;
+  }
+
+  FixArgs fix_args(const long long* idx, long long idx_gs, int n) const {
+    FixArgs f;
+    memset(&f, 0, sizeof(f));
+    f.priority = d_priority; f.prio_gs = cap_pad;
+    f.tile_sums = d_tile_sums; f.ts_gs = max_tiles;
+    f.super_sums = d_super_sums; f.ss_gs = max_supers;
+    f.idx = idx; f.idx_gs = idx_gs;
+    f.pos = 0; f.cap = capacity;
+    f.n = n;
+    return f;
+  }
+  // repair the sum tree for the entries of the last sample (their priorities were just rewritten)
+  int fix_sums_last_sample(int B, cudaStream_t stream) {
+    B200_LAUNCH(lap_fix_sums_kernel, dim3((unsigned)groups), dim3(1024), 0, stream, fix_args(d_idx, (long long)max_batch, B));
+    B200_CHECK_LAUNCH();
+    return kOk;
+  }
+  // rebuild the whole sum tree from the priorities
+  int rebuild_sums(long long n, cudaStream_t stream) {
+    const int ntiles = ceil_div((int)n, kPrioTile);
+    // nothing past `size` may contribute (a restored cursor can leave stale priorities behind it)
+    B200_CHECK_CUDA(cudaMemsetAsync(d_tile_sums, 0, (size_t)groups * max_tiles * sizeof(double), stream));
+    B200_CHECK_CUDA(cudaMemsetAsync(d_super_sums, 0, (size_t)groups * max_supers * sizeof(double), stream));
+    for (int g = 0; g < groups && n < cap_pad; ++g)
+      B200_CHECK_CUDA(cudaMemsetAsync(d_priority + (long long)g * cap_pad + n, 0, (size_t)(cap_pad - n) * sizeof(float), stream));
+    if (ntiles > 0) {
+      dim3 grid((unsigned)ceil_div(ntiles, kPrioTilesPerCta), (unsigned)groups), block(256);
+      B200_LAUNCH(lap_tile_sums_kernel, grid, block, 0, stream, d_priority, cap_pad, (int)n, d_tile_sums, ntiles, (long long)max_tiles);
+      B200_CHECK_LAUNCH();
+      const int nsup = ceil_div(ntiles, kSuperTiles);
+      dim3 grid2((unsigned)ceil_div(nsup, 8), (unsigned)groups);
+      B200_LAUNCH(lap_super_sums_kernel, grid2, block, 0, stream, d_tile_sums, (long long)max_tiles, d_super_sums, (long long)max_supers, nsup);
+      B200_CHECK_LAUNCH();
+    }
+    sums_valid = true;
     return kOk;
   }
 
@@ -321,15 +491,12 @@ struct Replay {
     B200_TRY(common_size(&n));
     if (n <= 0) { set_last_error("replay.sample: buffer is empty"); return kErrState; }
     const int ntiles = ceil_div((int)n, kPrioTile);
-    if (prioritized) {
-      dim3 grid((unsigned)ceil_div(ntiles, kPrioTilesPerCta), (unsigned)groups), block(256);
-      B200_LAUNCH(lap_tile_sums_kernel, grid, block, 0, stream, d_priority, cap_pad, (int)n, d_tile_sums, ntiles, (long long)max_tiles);
-      B200_CHECK_LAUNCH();
-    }
+    if (prioritized && !sums_valid) B200_TRY(rebuild_sums(n, stream));
     SampleArgs a;
     memset(&a, 0, sizeof(a));
     a.priority = d_priority; a.prio_gs = cap_pad;
     a.tile_sums = d_tile_sums; a.ts_gs = max_tiles; a.ntiles = ntiles;
+    a.super_sums = d_super_sums; a.ss_gs = max_supers; a.nsuper = ceil_div(ntiles, kSuperTiles);
     a.size = (int)n;
     a.u = u_dev; a.u_gs = B;
     a.seed = rng_seed; a.counter = counter_ptr ? 0ULL : rng_counter++; a.counter_ptr = counter_ptr;
@@ -342,10 +509,8 @@ struct Replay {
     a.done = o.done; a.done_gs = o.done_gs;
     a.B = B;
     a.prioritized = prioritized ? 1 : 0;
-    a.spw = samples_per_warp(groups);
-    dim3 grid((unsigned)ceil_div(B, 8 * a.spw), (unsigned)groups), block(256);
-    const size_t smem = prioritized ? (size_t)(ntiles + ntiles / 16 + 1) * sizeof(double) : 0;
-    B200_LAUNCH(lap_sample_kernel, grid, block, smem, stream, a);
+    dim3 grid((unsigned)ceil_div(B, 8), (unsigned)groups), block(256);
+    B200_LAUNCH(lap_sample_kernel, grid, block, 0, stream, a);
     B200_CHECK_LAUNCH();
     last_batch = B;
     return kOk;
@@ -357,7 +522,7 @@ struct Replay {
     B200_REQUIRE(B == last_batch, "update_priority: batch size differs from the last sample()");
     dim3 grid((unsigned)groups), block((unsigned)round_up(B, 32));
     B200_LAUNCH(lap_update_priority_kernel, grid, block, sizeof(ScatterTable), stream, d_priority, cap_pad, d_max_priority, d_idx,
-                (long long)max_batch, prio_dev, p_gs, B);
+                (long long)max_batch, prio_dev, p_gs, B, fix_args(d_idx, (long long)max_batch, sums_valid ? B : 0));
     B200_CHECK_LAUNCH();
     return kOk;
   }

@@ -3,6 +3,7 @@ glue between the Python-visible state (``rl.nn`` modules, counters) and the devi
 from __future__ import annotations
 
 import copy
+import weakref
 import ctypes as C
 import os
 import pickle
@@ -61,6 +62,14 @@ class LazyScalar:
     def __repr__(self): return repr(float(self))
 
 
+class _DeviceView:
+    """``__cuda_array_interface__`` holder for a float32 region of engine-owned device memory."""
+
+    def __init__(self, ptr: int, shape, owner):
+        self._owner = owner  # keeps the engine (and with it the memory) alive
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2, "strides": None}
+
+
 class Agent(ABC):
     """Common machinery of the TD7 / TD3 / SAC drop-ins."""
 
@@ -79,6 +88,7 @@ class Agent(ABC):
         self._dirty_host = True   # host modules newer than device blobs
         self._dirty_dev = False   # device blobs newer than host modules
         self._info_cache = {}
+        self._inbox = None
         self._create_engine()
         self._push()
 
@@ -224,11 +234,12 @@ class Agent(ABC):
         memo[id(self)] = new
         self._pull()
         for k, v in self.__dict__.items():
-            if k in ("_h", "_lib", "_info_cache"):
+            if k in ("_h", "_lib", "_info_cache", "_inbox"):
                 continue
             setattr(new, k, copy.deepcopy(v, memo))
         new._lib = self._lib
         new._h = None
+        new._inbox = None
         new._info_cache = {}
         new._create_engine()
         _lib.check(new._lib.b200rl_agent_copy_from(new._h, self._h, 1, _stream()))
@@ -239,7 +250,7 @@ class Agent(ABC):
     # materialised as plain tensors
     def __getstate__(self):
         self._pull()
-        d = {k: v for k, v in self.__dict__.items() if k not in ("_h", "_lib", "_info_cache")}
+        d = {k: v for k, v in self.__dict__.items() if k not in ("_h", "_lib", "_info_cache", "_inbox")}
         extra = {}
         if self._h:
             for nid, (attr, _) in enumerate(self.NETS):
@@ -255,7 +266,7 @@ class Agent(ABC):
     def __setstate__(self, d):
         extra = d.pop("_pickled_engine_state", {})
         self.__dict__.update(d)
-        self._h, self._info_cache = None, {}
+        self._h, self._info_cache, self._inbox = None, {}, None
         self._lib = _lib.lib()
         self._create_engine()
         self._push()
@@ -291,15 +302,39 @@ class Agent(ABC):
             return pickle.load(fh)
 
     # ------------------------------------------------------------------ the update
+    def _make_inbox(self):
+        """Tensors aliasing the engine's fixed input buffers (single seed): what replay.sample() returns once
+        this agent is the buffer's sink, so that train_ops(batch) needs no staging copy."""
+        ss, ac, rw, nd, gs = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
+        _lib.check(self._lib.b200rl_agent_io(self._h, C.byref(ss), C.byref(ac), C.byref(rw), C.byref(nd), C.byref(gs)))
+        B, S, A = self.batch_size, self.state_dim, self.action_dim
+        view = lambda ptr, shape: torch.as_tensor(_DeviceView(ptr, shape, self), device=self.device)  # noqa: E731
+        return {"state": view(ss.value, (B, S)), "action": view(ac.value, (B, A)), "reward": view(rw.value, (B, 1)),
+                "next_state": view(ss.value + 4 * B * S, (B, S)), "done": view(nd.value, (B, 1))}
+
+    def _adopt_sink(self, replay_buffer):
+        if replay_buffer is None or self.n_seeds != 1 or not getattr(replay_buffer, "zero_copy", False):
+            return
+        if getattr(replay_buffer, "n_seeds", 1) != 1 or not hasattr(replay_buffer, "_sink"):
+            return
+        cur = replay_buffer._sink() if replay_buffer._sink is not None else None
+        if cur is not self:
+            if self._inbox is None:
+                self._inbox = self._make_inbox()
+            replay_buffer._sink = weakref.ref(self)
+
     def _stage(self, batch):
+        if batch is self._inbox and batch is not None:
+            return batch  # sampled straight into the engine's input buffers
         dev = self.device
         t = {k: torch.as_tensor(v, dtype=torch.float32).to(dev, non_blocking=True).contiguous() for k, v in batch.items()}
         _lib.check(self._lib.b200rl_agent_stage_batch(self._h, 0, t["state"].data_ptr(), t["action"].data_ptr(), t["reward"].data_ptr(),
                                                       t["next_state"].data_ptr(), t["done"].data_ptr(), _stream()))
         return t
 
-    def _update(self, replay_buffer, noise):
+    def _update(self, replay_buffer, noise, sink=None):
         self._flush()
+        self._adopt_sink(sink)
         rh = getattr(replay_buffer, "_h", None) if replay_buffer is not None else None
         nz = None
         if noise is not None:

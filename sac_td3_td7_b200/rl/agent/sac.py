@@ -100,7 +100,7 @@ class SAC(_MlpAgent):
         self._stage(batch)
         if noise is not None and isinstance(noise, (tuple, list)):
             noise = torch.stack([torch.as_tensor(noise[0]), torch.as_tensor(noise[1])])
-        self._update(None, noise)
+        self._update(None, noise, sink=replay_buffer)
         return self._info_dict(self._n_calls, True)
 
     @torch.no_grad()

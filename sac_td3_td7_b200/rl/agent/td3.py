@@ -111,7 +111,7 @@ class TD3(_MlpAgent):
         if self.use_lap:
             assert isinstance(replay_buffer, LAPReplayMemory)
         self._stage(batch)
-        self._update(replay_buffer if self.use_lap else None, noise)
+        self._update(replay_buffer if self.use_lap else None, noise, sink=replay_buffer)
         return self._info_dict(self._n_calls, self._actor_step(self._n_calls))
 
     def sample(self, state, deterministic: bool = False, **kwargs) -> np.ndarray:

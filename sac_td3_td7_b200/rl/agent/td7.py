@@ -130,7 +130,7 @@ class TD7(Agent):
         if self.use_lap:
             assert isinstance(replay_buffer, LAPReplayMemory)  # td7.py:310
         self._stage(batch)
-        self._update(replay_buffer if self.use_lap else None, noise)
+        self._update(replay_buffer if self.use_lap else None, noise, sink=replay_buffer)
         return self._info_dict(self._n_calls, self._actor_step(self._n_calls))
 
     def sample(self, state, deterministic: bool = False, **kwargs) -> np.ndarray:

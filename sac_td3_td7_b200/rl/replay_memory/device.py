@@ -29,7 +29,7 @@ class _DeviceRing(BaseReplayMemory):
     prioritized = True
 
     def __init__(self, replay_buffer_size: int, env_id: str | None = None, *, state_dim=None, action_dim=None,
-                 n_seeds: int = 1, share_rows: bool = False, device="cuda", **kwargs) -> None:
+                 n_seeds: int = 1, share_rows: bool = False, device="cuda", zero_copy: bool = True, **kwargs) -> None:
         super().__init__(replay_buffer_size, **kwargs)
         if not torch.cuda.is_available():
             raise _lib.B200RLError("sac_td3_td7_b200 replay memory needs a CUDA device (no CPU fallback)")
@@ -47,6 +47,11 @@ class _DeviceRing(BaseReplayMemory):
         self.size = 0
         self._last_batch = 0
         self._row = np.zeros((1, self.row_stride), np.float32)
+        # zero-copy hand-off: once an agent has trained from this buffer (train_ops(batch, replay_buffer=self)),
+        # sample() writes straight into that agent's fixed input buffers and returns tensors that ALIAS them --
+        # the next sample() overwrites them.  zero_copy=False restores private tensors per call.
+        self.zero_copy = bool(zero_copy)
+        self._sink = None  # weakref to the agent whose input buffers sample() fills
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -119,6 +124,16 @@ class _DeviceRing(BaseReplayMemory):
     def sample(self, batch_size: int, use_torch: bool = True, u: torch.Tensor | None = None, out: dict | None = None):
         """lap.py:45-64.  Returns fp32 CUDA tensors [B, dim] ([n_seeds, B, dim] when stacked)."""
         B, G, S, A = int(batch_size), self.n_seeds, self.state_dim, self.action_dim
+        sink = self._sink() if self._sink is not None else None
+        if sink is not None and out is None and use_torch and sink._h and B == sink.batch_size and sink._inbox is not None:
+            u_ptr = None
+            if u is not None:
+                u = torch.as_tensor(u, dtype=torch.float32).to(self.device).contiguous()
+                assert u.numel() == B
+                u_ptr = u.data_ptr()
+            _lib.check(self._lib.b200rl_replay_sample_to_agent(self._h, sink._h, B, u_ptr, _stream()))
+            self._last_batch = B
+            return sink._inbox
         if out is None:
             shape = (lambda d: (B, d)) if G == 1 else (lambda d: (G, B, d))
             out = dict(state=torch.empty(shape(S), device=self.device), action=torch.empty(shape(A), device=self.device),

@@ -143,6 +143,46 @@ def test_append_from_rollout_and_uniform_buffer():
         assert torch.equal(b[k].cpu(), rb[k]), k
 
 
+def test_zero_copy_sample_hand_off():
+    """After the first train_ops(batch, replay_buffer=buf) the buffer samples straight into the agent's input
+    buffers: sample() returns tensors aliasing them (same dict every call), the results are those of the
+    staged path, and a buffer created with zero_copy=False keeps handing out private tensors."""
+    from sac_td3_td7_b200.rl.agent import TD7
+    from sac_td3_td7_b200.rl.replay_memory import LAPReplayMemory
+
+    def run(zero_copy):
+        torch.manual_seed(7)
+        agent = TD7("Hopper-v4", use_lap=True)
+        buf = LAPReplayMemory(4096, "Hopper-v4", zero_copy=zero_copy)
+        buf.fill_synthetic(4000, seed=1)
+        g = torch.Generator().manual_seed(3)
+        out, batches = [], []
+        for t in range(6):
+            u = torch.rand(256, generator=g)
+            nz = torch.randn(256, agent.action_dim, generator=g)
+            batch = buf.sample(256, u=u)
+            batches.append(batch)
+            ind = buf.ind.copy()
+            info = agent.train_ops(batch, replay_buffer=buf, noise=nz)
+            out.append((ind, batch["reward"].cpu().numpy().copy(), float(info["train/q_fn"]), buf.max_priority))
+        return agent, buf, out, batches
+
+    a1, b1, o1, batches1 = run(True)
+    a0, b0, o0, batches0 = run(False)
+    for x, y in zip(o1, o0):
+        assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]) and x[2] == y[2] and x[3] == y[3]
+    assert batches1[1] is a1._inbox and batches1[2] is batches1[1]          # aliasing, from the second call on
+    assert batches1[1]["next_state"].data_ptr() == batches1[1]["state"].data_ptr() + 4 * 256 * a1.state_dim
+    assert batches0[1] is not batches0[2] and a0._inbox is None or batches0[1] is not a0._inbox
+    # another agent fed from the same buffer takes the staged path and then becomes the sink
+    other = TD7("Hopper-v4", use_lap=True)
+    batch = b1.sample(256)
+    assert batch is a1._inbox
+    info = other.train_ops(batch, replay_buffer=b1)
+    assert np.isfinite(float(info["train/q_fn"]))
+    assert b1.sample(256) is other._inbox
+
+
 def test_no_cpu_fallback_paths():
     from sac_td3_td7_b200 import _lib
     from sac_td3_td7_b200.rl import nn as bnn

@@ -98,6 +98,41 @@ def test_append_ring_wrap_scatter_and_running_max(dev):
     dev.check(dev.lib.b200rl_replay_destroy(h))
 
 
+def test_incrementally_repaired_sum_tree_tracks_the_oracle(dev):
+    """The sampler's sum tree is repaired in place by append / update_priority; after many rounds of
+    {append a few rows (crossing tile, super-tile and ring boundaries), sample, write priorities back}
+    the indices must still be the reference's (torch.cumsum + searchsorted on the whole array)."""
+    cap = 40_000  # 157 tiles, 3 super-tiles; not a multiple of the tile size
+    h = dev.replay_create(cap, S, A)
+    ref = oreplay.OracleLAP(cap, "Hopper-v4")
+    rng = np.random.default_rng(77)
+
+    def rows(n):
+        obs, act = rng.standard_normal((n, S)).astype(np.float32), rng.uniform(-1, 1, (n, A)).astype(np.float32)
+        rew, nobs, nd = rng.standard_normal(n).astype(np.float32), rng.standard_normal((n, S)).astype(np.float32), (rng.random(n) > 0.1).astype(np.float32)
+        for i in range(n):
+            ref.append([obs[i], act[i], float(rew[i]), nobs[i], float(nd[i])])
+        return dev.pack_rows(h, obs, (act / ref.action_scale - ref.action_bias).astype(np.float32), rew, nobs, nd)
+
+    dev.replay_append(h, rows(39_000))  # bulk: invalidates the tree, the first sample rebuilds it
+    B = 96
+    for rnd in range(40):
+        n_new = [1, 3, 300, 1, 700, 5][rnd % 6]  # from round ~2 on the ring wraps
+        dev.replay_append(h, rows(n_new))
+        u = rng.random(B).astype(np.float32)
+        if rnd % 7 == 0:
+            u[:3] = [0.0, np.nextafter(np.float32(1), np.float32(0)), 0.5]
+        idx, _, _ = dev.replay_sample(h, B, S, A, u=u)
+        ref.sample(B, u=torch.tensor(u))
+        assert np.array_equal(idx[0], ref.ind), f"round {rnd}"
+        pr = (np.maximum(np.abs(rng.standard_normal(B)) * 4, 1.0) ** 0.4).astype(np.float32)
+        dev.check(dev.lib.b200rl_replay_update_priority(h, dev.to_dev(pr), B, None))
+        ref.update_priority(torch.tensor(pr))
+    assert np.array_equal(dev.replay_priority(h, cap), ref.priority.numpy().astype(np.float32))
+    assert dev.replay_state(h)[2] == float(ref.max_priority)
+    dev.check(dev.lib.b200rl_replay_destroy(h))
+
+
 def test_duplicate_scatter_last_wins_and_reset(dev):
     g = gu.load("replay_cases")
     cap = 3000
