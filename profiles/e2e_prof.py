@@ -1,5 +1,5 @@
 import time, sys, numpy as np, torch
-sys.path.insert(0, ".")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from sac_td3_td7_b200.rl.agent import TD7
 from sac_td3_td7_b200.rl.replay_memory import LAPReplayMemory
 env = "HalfCheetah-v4"; S, A = 17, 6

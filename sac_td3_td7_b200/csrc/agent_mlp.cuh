@@ -173,10 +173,8 @@ struct MlpAgent : AgentBase {
     a.st = d_step;
     a.gamma = (float)cfg.discount;
     a.B = B; a.use_lap = use_lap ? 1 : 0; a.gs = act_stride;
-    if (use_lap && bound) {
-      a.priority = bound->d_priority; a.max_priority = bound->d_max_priority; a.idx = bound->d_idx; a.prio_gs = bound->cap_pad;
-      a.idx_gs = bound->max_batch;
-    }
+    // (the LAP write-back itself -- last-writer-wins scatter, running max, sum-tree repair -- is a separate node beside the
+    // backward pass: Replay::scatter_and_fix on the priorities left in prio_dbg)
     B200_LAUNCH(critic_loss_kernel, dim3((unsigned)G), dim3((unsigned)round_up(B, 32)), sizeof(ScatterTable), s, a);
     B200_CHECK_LAUNCH();
     return kOk;
@@ -236,10 +234,10 @@ struct MlpAgent : AgentBase {
     }
     GL(Tq[0], M); GL(Tq[1], M); GL(Tq[2], M);
     B200_TRY(launch_critic_loss(M));
-    const bool fix_tree = use_lap && bound != nullptr;  // the write-back changed <= B priorities: repair the sampler's sum tree off the chain
+    const bool fix_tree = use_lap && bound != nullptr;  // LAP write-back + sum-tree repair, off the chain
     if (fix_tree) {
       B200_TRY(fork.link(M, sP));
-      B200_TRY(bound->fix_sums_last_sample(B, sP));
+      B200_TRY(bound->scatter_and_fix(prio_dbg.p, act_stride, B, sP));
     }
     GL(Td[0], M); GL(Td[1], M); GL(Tw, M);
     if (sac) B200_TRY(fork.link(sN, M));

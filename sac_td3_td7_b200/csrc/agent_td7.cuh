@@ -44,7 +44,10 @@ struct TD7Agent : AgentBase {
 
   // launch tables
   GemmTable E[16], C[24], Aa[24];
+  GemmTable C2v[2];        // second launch of the critic chain, without / with the actor step's l0(s)
+  GemmTable Wq[4], Wp[4];  // critic / policy weight gradients (+Adam), one launch per layer: [0] = last layer
   RowTable En[2], Cn[4], An[4];
+  RowTable CnQ, CnP[2];
 
   void layout_acts() {
     act_cursor = 0;
@@ -151,16 +154,18 @@ struct TD7Agent : AgentBase {
       B200_TRY(up(E[11], kWgrad, w));
     }
     // ------------------------------------------------ critic chain (td7.py:175-244, 307-315)
+    // first launch: 4 x 64 tiles = one wave at 2 CTAs per SM; the policy's l0 rides with the second launch (128 tiles)
+    B200_TRY(up(C[0], kFwd, PV{fwd_problem(fet, 0, {s_nxt}, t1, kActElu), fwd_problem(fe, 0, {s_cur}, f1, kActElu),
+                               fwd_problem(q[0], 0, {s_cur, act_in}, cq0[0], kActNone), fwd_problem(q[1], 0, {s_cur, act_in}, cq0[1], kActNone)}));
+    B200_TRY(upn(CnQ, false, {nf(cq0[0], cq0n[0]), nf(cq0[1], cq0n[1])}));
     {
-      PV c1{fwd_problem(fet, 0, {s_nxt}, t1, kActElu), fwd_problem(fe, 0, {s_cur}, f1, kActElu), fwd_problem(pol, 0, {s_nxt}, pa0, kActNone),
-            fwd_problem(q[0], 0, {s_cur, act_in}, cq0[0], kActNone), fwd_problem(q[1], 0, {s_cur, act_in}, cq0[1], kActNone)};
-      B200_TRY(up(C[0], kFwd, c1));
-      c1.push_back(fwd_problem(pol, 0, {s_cur}, pb0, kActNone));  // actor steps also need l0(s)
-      B200_TRY(up(C[1], kFwd, c1));
+      PV c2{fwd_problem(fet, 1, {t1}, t2, kActElu), fwd_problem(fe, 1, {f1}, f2, kActElu), fwd_problem(pol, 0, {s_nxt}, pa0, kActNone)};
+      B200_TRY(up(C2v[0], kFwd, c2));
+      c2.push_back(fwd_problem(pol, 0, {s_cur}, pb0, kActNone));  // actor steps also need l0(s)
+      B200_TRY(up(C2v[1], kFwd, c2));
     }
-    B200_TRY(upn(Cn[0], false, {nf(pa0, pa0n), nf(cq0[0], cq0n[0]), nf(cq0[1], cq0n[1])}));
-    B200_TRY(upn(Cn[1], false, {nf(pa0, pa0n), nf(cq0[0], cq0n[0]), nf(cq0[1], cq0n[1]), nf(pb0, pb0n)}));
-    B200_TRY(up(C[2], kFwd, PV{fwd_problem(fet, 1, {t1}, t2, kActElu), fwd_problem(fe, 1, {f1}, f2, kActElu)}));
+    B200_TRY(upn(CnP[0], false, {nf(pa0, pa0n)}));
+    B200_TRY(upn(CnP[1], false, {nf(pa0, pa0n), nf(pb0, pb0n)}));
     B200_TRY(up(C[3], kFwd, PV{fwd_problem(fet, 2, {t2}, tu3, kActNone), fwd_problem(fe, 2, {f2}, fu3, kActNone)}));
     B200_TRY(upn(Cn[2], false, {nf(tu3, zs_t), nf(fu3, zs_f)}));
     B200_TRY(up(C[4], kFwd, PV{fwd_problem(pol, 1, {pa0n, zs_t}, p1, kActRelu), fwd_problem(fe, 3, {zs_f, act_in}, fa1, kActElu)}));
@@ -185,14 +190,19 @@ struct TD7Agent : AgentBase {
     {
       std::vector<RowOp> nbq{nb(cq0[0], d_cq0n[0], d_cq0[0]), nb(cq0[1], d_cq0n[1], d_cq0[1])};
       B200_TRY(row_table_upload(&critic_norm_bwd, true, nbq, &arena));
-      PV w;
+      // one launch per layer: layer l's gradient (and its in-place Adam step) can start as soon as the dgrad that READS
+      // layer l's weights has finished, instead of waiting for the whole backward chain
+      PV w3, w2, w1, w0;
       for (int k = 0; k < 2; ++k) {
-        wgrad_problems(w, q[k], 3, dq[k], {cqb[k]}, true);
-        wgrad_problems(w, q[k], 2, d_cqb[k], {cqa[k]}, true);
-        wgrad_problems(w, q[k], 1, d_cqa[k], {cq0n[k], zsa_f, zs_f}, true);
-        wgrad_problems(w, q[k], 0, d_cq0[k], {s_cur, act_in}, true);
+        wgrad_problems(w3, q[k], 3, dq[k], {cqb[k]}, true);
+        wgrad_problems(w2, q[k], 2, d_cqb[k], {cqa[k]}, true);
+        wgrad_problems(w1, q[k], 1, d_cqa[k], {cq0n[k], zsa_f, zs_f}, true);
+        wgrad_problems(w0, q[k], 0, d_cq0[k], {s_cur, act_in}, true);
       }
-      B200_TRY(up(C[16], kWgrad, w));
+      B200_TRY(up(Wq[0], kWgrad, w3));
+      B200_TRY(up(Wq[1], kWgrad, w2));
+      B200_TRY(up(Wq[2], kWgrad, w1));
+      B200_TRY(up(Wq[3], kWgrad, w0));
     }
     // ------------------------------------------------ actor step (td7.py:259-276, 319-324)
     B200_TRY(up(Aa[0], kFwd, PV{fwd_problem(pol, 1, {pb0n, zs_f}, pp1, kActRelu)}));
@@ -220,12 +230,15 @@ struct TD7Agent : AgentBase {
     B200_TRY(up(Aa[18], kDgrad, PV{dgrad_problem({{&pol, 1, d_pp1, 0}}, H, d_pb0n, nullptr, 0)}));
     B200_TRY(upn(An[2], true, {nb(pb0, d_pb0n, d_pb0)}));
     {
-      PV w;
-      wgrad_problems(w, pol, 3, d_api, {pp2}, true);
-      wgrad_problems(w, pol, 2, d_pp2, {pp1}, true);
-      wgrad_problems(w, pol, 1, d_pp1, {pb0n, zs_f}, true);
-      wgrad_problems(w, pol, 0, d_pb0, {s_cur}, true);
-      B200_TRY(up(Aa[19], kWgrad, w));
+      PV w3, w2, w1, w0;
+      wgrad_problems(w3, pol, 3, d_api, {pp2}, true);
+      wgrad_problems(w2, pol, 2, d_pp2, {pp1}, true);
+      wgrad_problems(w1, pol, 1, d_pp1, {pb0n, zs_f}, true);
+      wgrad_problems(w0, pol, 0, d_pb0, {s_cur}, true);
+      B200_TRY(up(Wp[0], kWgrad, w3));
+      B200_TRY(up(Wp[1], kWgrad, w2));
+      B200_TRY(up(Wp[2], kWgrad, w1));
+      B200_TRY(up(Wp[3], kWgrad, w0));
     }
     built = true;
     return kOk;
@@ -254,9 +267,8 @@ struct TD7Agent : AgentBase {
     a.st = d_step;
     a.gamma = (float)cfg.discount;
     a.B = B; a.use_lap = use_lap ? 1 : 0; a.huber_sum = 1; a.gs = act_stride;
-    if (use_lap && bound) {
-      a.priority = bound->d_priority; a.max_priority = bound->d_max_priority; a.idx = bound->d_idx; a.prio_gs = bound->cap_pad;
-    }
+    // (the LAP write-back itself -- last-writer-wins scatter, running max, sum-tree repair -- is a separate node beside the
+    // backward pass: Replay::scatter_and_fix on the priorities left in prio_dbg)
     a.idx_gs = bound ? (long long)bound->max_batch : 0;
     B200_LAUNCH(critic_loss_kernel, dim3((unsigned)G), dim3((unsigned)round_up(B, 32)), sizeof(ScatterTable), s, a);
     B200_CHECK_LAUNCH();
@@ -287,10 +299,13 @@ struct TD7Agent : AgentBase {
     GL(E[6], sE); GL(E[7], sE); GL(E[8], sE); RL(En[1], sE); GL(E[9], sE); GL(E[10], sE); GL(E[11], sE);
     }
     // ---- critic chain
-    GL(actor ? C[1] : C[0], M);
+    GL(C[0], M);
     B200_TRY(fork.link(M, sN));
-    RL(actor ? Cn[1] : Cn[0], sN);
-    GL(C[2], M); GL(C[3], M); RL(Cn[2], M);
+    RL(CnQ, sN);
+    GL(C2v[actor ? 1 : 0], M);
+    B200_TRY(fork.link(M, sN));
+    RL(CnP[actor ? 1 : 0], sN);
+    GL(C[3], M); RL(Cn[2], M);
     B200_TRY(fork.link(sN, M));
     if (actor) {  // hoisted part of the actor step: needs zs_f, pb0n, the (unchanged) policy and fixed encoder
       B200_TRY(fork.link(M, sA));
@@ -305,12 +320,19 @@ struct TD7Agent : AgentBase {
     B200_TRY(fork.link(sN, M));
     GL(C[10], M); GL(C[11], M); GL(C[12], M);
     B200_TRY(launch_critic_loss(M));
-    const bool fix_tree = use_lap && bound != nullptr;  // the write-back changed <= B priorities: repair the sampler's sum tree off the chain
+    const bool fix_tree = use_lap && bound != nullptr;  // LAP write-back + sum-tree repair, off the chain
     if (fix_tree) {
       B200_TRY(fork.link(M, sP));
-      B200_TRY(bound->fix_sums_last_sample(B, sP));
+      B200_TRY(bound->scatter_and_fix(prio_dbg.p, act_stride, B, sP));
     }
-    GL(C[13], M); GL(C[14], M); GL(C[15], M); RL(critic_norm_bwd, M); GL(C[16], M);
+    GL(C[13], M);
+    B200_TRY(fork.link(M, sN)); GL(Wq[0], sN);  // q3 weights were last read by C[13]
+    GL(C[14], M);
+    B200_TRY(fork.link(M, sN)); GL(Wq[1], sN);
+    GL(C[15], M);
+    B200_TRY(fork.link(M, sN)); GL(Wq[2], sN);
+    RL(critic_norm_bwd, M); GL(Wq[3], M);
+    B200_TRY(fork.link(sN, M));
     if (actor) {
       B200_TRY(fork.link(sA, M));
       GL(Aa[6], M); RL(An[0], M); GL(Aa[7], M); GL(Aa[8], M);
@@ -323,7 +345,14 @@ struct TD7Agent : AgentBase {
       RL(An[1], sN);
       GL(Aa[13], M); GL(Aa[14], M);
       B200_TRY(fork.link(sN, M));
-      GL(Aa[15], M); GL(Aa[16], M); GL(Aa[17], M); GL(Aa[18], M); RL(An[2], M); GL(Aa[19], M);
+      GL(Aa[15], M); GL(Aa[16], M);
+      B200_TRY(fork.link(M, sN)); GL(Wp[0], sN);  // l3 weights were last read by Aa[16]
+      GL(Aa[17], M);
+      B200_TRY(fork.link(M, sN)); GL(Wp[1], sN);
+      GL(Aa[18], M);
+      B200_TRY(fork.link(M, sN)); GL(Wp[2], sN);
+      RL(An[2], M); GL(Wp[3], M);
+      B200_TRY(fork.link(sN, M));
     }
     B200_TRY(fork.link(sE, M));
     if (fix_tree) B200_TRY(fork.link(sP, M));

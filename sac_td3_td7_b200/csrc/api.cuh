@@ -549,6 +549,14 @@ int b200rl_op_gemm(int mode, const b200rl_gemm_problem* problems_host, int nprob
   return kOk;
 }
 #ifdef B200RL_PROBE
+// out[256][2] = {earliest CTA entry, latest CTA exit} (ns, global timer) per table since the last call; resets the slots
+int b200rl_debug_timeline(unsigned long long* out256x2) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out256x2, g_tl, sizeof(unsigned long long) * 512) != cudaSuccess) return 1;
+  static unsigned long long init[256][2];
+  for (auto& e : init) { e[0] = ~0ull; e[1] = 0ull; }
+  return cudaMemcpyToSymbol(g_tl, init, sizeof(init)) == cudaSuccess ? 0 : 1;
+}
 int b200rl_debug_probe(long long* out64x10) {
   cudaDeviceSynchronize();
   return cudaMemcpyFromSymbol(out64x10, g_probe, sizeof(long long) * 640) == cudaSuccess ? 0 : 1;

@@ -145,6 +145,8 @@ struct FfmaLaunch {
   FfmaProblem p[kMaxProblems];
   int nprob;
   int splitk;
+  int tag;  // table number in creation order (profiling builds: timeline slot)
+  int pad;
 };
 
 constexpr int kTile = 32;   // output tile edge
@@ -323,7 +325,20 @@ __device__ unsigned g_probe_n;
 #define B200_PROBE_DECL long long pb_[10]; const bool pb_on_ = (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0); if (pb_on_) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pb_[0])); pb_[1] = clock64(); }
 #define B200_PROBE(i) if (pb_on_) pb_[i] = clock64();
 #define B200_PROBE_END if (pb_on_) { pb_[8] = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pb_[9])); unsigned sl_ = atomicAdd(&g_probe_n, 1u) & 63u; for (int q_ = 0; q_ < 10; ++q_) g_probe[sl_][q_] = pb_[q_]; }
+// per-table timeline: earliest CTA entry / latest CTA exit of the most recent launch of every table (tag)
+__device__ unsigned long long g_tl[256][2];
+struct TimelineGuard {
+  int tag;
+  __device__ explicit TimelineGuard(int t) : tag(t & 255) {
+    if (threadIdx.x == 0) { unsigned long long n; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(n)); atomicMin(&g_tl[tag][0], n); }
+  }
+  __device__ ~TimelineGuard() {
+    if (threadIdx.x == 0) { unsigned long long n; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(n)); atomicMax(&g_tl[tag][1], n); }
+  }
+};
+#define B200_TIMELINE(tag) TimelineGuard tl_guard_(tag);
 #else
+#define B200_TIMELINE(tag)
 #define B200_PROBE_DECL
 #define B200_PROBE(i)
 #define B200_PROBE_END
@@ -352,6 +367,23 @@ __device__ __forceinline__ void st_cluster_f4(float* local, unsigned rank, float
 }
 #endif
 
+// Two fp32 FMAs in one instruction (Blackwell FFMA2, PTX fma.rn.f32x2): d.x = a.x*b.x + d.x, d.y = a.y*b.y + d.y,
+// each rounded to nearest exactly like fmaf.  Half the issue slots and register-file reads of two FFMAs, which is
+// what the small-tile main loop is short of.
+__device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
+#ifdef B200_EMU
+  d.x = fmaf(a.x, b.x, d.x);
+  d.y = fmaf(a.y, b.y, d.y);
+#else
+  unsigned long long dd, aa, bb;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(dd) : "f"(d.x), "f"(d.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(bb) : "f"(b.x), "f"(b.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(bb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(dd));
+#endif
+}
+
 // four consecutive floats of an epilogue operand, all loads in flight at once
 __device__ __forceinline__ void load_quad(float (&o)[4], const float* p, int nvalid) {
   if (nvalid == 4 && aligned16(p)) {
@@ -378,6 +410,7 @@ template <int MODE, int MINB>
 __global__ void __launch_bounds__(kGemmThreads, MINB) gemm_kernel(const __grid_constant__ FfmaLaunch L) {
   B200_PDL_TRIGGER();  // the setup below reads kernel parameters only: it may overlap the previous kernel
   B200_PROBE_DECL
+  B200_TIMELINE(L.tag)
   constexpr bool A_KM = (MODE != kWgrad);  // A contiguous along the reduction in global memory
   constexpr bool B_KM = (MODE == kFwd);
   // 3 pipeline stages x (A tile 32x64, B tile 32x64) = 48 KB; the first 32 KB later hold the 8 partial tiles;
@@ -409,11 +442,19 @@ __global__ void __launch_bounds__(kGemmThreads, MINB) gemm_kernel(const __grid_c
   const int warp = tid >> 5, lane = tid & 31;
   const int li = lane >> 2, lj = lane & 3;
 
+  // dgrad / wgrad read B contiguous along the output column, so neighbouring outputs (a, 2bp) and (a, 2bp+1) sit in
+  // adjacent registers and one FFMA2 updates both (same r order, same rounding as two FFMAs).  Forward reads both
+  // operands contiguous along r; pairing there would need split even/odd accumulators (64 more registers): plain FFMA.
+  constexpr bool USE_F2 = (MODE != kFwd);
+  float2 acc2[4][4];
   float acc[4][8];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < 4; ++a) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc2[a][b] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+  }
 
   // this CTA's slice of the flattened (segment, chunk) sequence
   const int c_begin = split * sp.per_split;
@@ -529,12 +570,23 @@ __global__ void __launch_bounds__(kGemmThreads, MINB) gemm_kernel(const __grid_c
           bv[4][rr] = v1.x; bv[5][rr] = v1.y; bv[6][rr] = v1.z; bv[7][rr] = v1.w;
         }
       }
+      if (!USE_F2) {
 #pragma unroll
-      for (int rr = 0; rr < 4; ++rr)
+        for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+          for (int a = 0; a < 4; ++a)
 #pragma unroll
-          for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(av[a][rr], bv[b][rr], acc[a][b]);
+            for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(av[a][rr], bv[b][rr], acc[a][b]);
+      } else {
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const float2 aa = make_float2(av[a][rr], av[a][rr]);
+#pragma unroll
+            for (int bp = 0; bp < 4; ++bp) ffma2(acc2[a][bp], aa, make_float2(bv[2 * bp][rr], bv[2 * bp + 1][rr]));
+          }
+      }
     }
   }
 
@@ -577,6 +629,12 @@ __global__ void __launch_bounds__(kGemmThreads, MINB) gemm_kernel(const __grid_c
   // ---- cross-warp reduction of the eight K-slices, fixed order (bit-reproducible) ----
   // partial tile layout: [warp][row][8 slots of float4], slot index XOR (row >> 2) to spread banks
   float* part = smem;
+  if (USE_F2) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) acc[a][b] = (b & 1) ? acc2[a][b >> 1].y : acc2[a][b >> 1].x;
+  }
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     const int row = li * 4 + a;

@@ -167,11 +167,13 @@ inline int gemm_table_upload(GemmTable* t, int mode, std::vector<GemmProblem>& p
   for (size_t i = 0; i < tc.size(); ++i) t->launch_tc.p[i] = tc[i];
   t->launch.nprob = (int)ff.size();
   t->launch.splitk = splitk;
+  static int table_counter = 0;
+  t->launch.tag = ++table_counter;
   if (getenv("B200RL_DEBUG_TABLES")) {
     int mc = 0;
     for (auto& p : ff) mc = std::max(mc, chunks_of(p));
-    fprintf(stderr, "[b200rl] gemm table mode=%d problems=%zu (+%zu tc) tiles=%d groups=%d max_chunks=%d splitk=%d\n", mode, ff.size(), tc.size(), tiles, groups, mc,
-            splitk);
+    fprintf(stderr, "[b200rl] gemm table %d mode=%d problems=%zu (+%zu tc) tiles=%d groups=%d max_chunks=%d splitk=%d\n", t->launch.tag, mode, ff.size(),
+            tc.size(), tiles, groups, mc, splitk);
   }
   t->launch_tc.nprob = (int)tc.size();
   t->launch_tc.total_tiles = tct;

@@ -440,9 +440,11 @@ struct Replay {
     f.n = n;
     return f;
   }
-  // repair the sum tree for the entries of the last sample (their priorities were just rewritten)
-  int fix_sums_last_sample(int B, cudaStream_t stream) {
-    B200_LAUNCH(lap_fix_sums_kernel, dim3((unsigned)groups), dim3(1024), 0, stream, fix_args(d_idx, (long long)max_batch, B));
+  // priority write-back for the indices of the last sample + repair of the sum tree, as one kernel (graph node of
+  // the agents' update: runs beside the critic's backward pass, off the critical chain)
+  int scatter_and_fix(const float* prio_dev, long long p_gs, int B, cudaStream_t stream) {
+    B200_LAUNCH(lap_update_priority_kernel, dim3((unsigned)groups), dim3(1024), sizeof(ScatterTable), stream, d_priority, cap_pad, d_max_priority, d_idx,
+                (long long)max_batch, prio_dev, p_gs, B, fix_args(d_idx, (long long)max_batch, B));
     B200_CHECK_LAUNCH();
     return kOk;
   }
