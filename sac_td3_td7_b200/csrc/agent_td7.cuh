@@ -114,10 +114,12 @@ struct TD7Agent : AgentBase {
     return kOk;
   }
 
+  // side = the launch belongs to a branch with slack (encoder step, hoisted actor forward): no split-K there, so that
+  // it takes as few SMs as possible away from the critical chain it runs beside
   template <class V>
-  int up(GemmTable& t, int mode, V probs) {
+  int up(GemmTable& t, int mode, V probs, bool side = false) {
     std::vector<GemmProblem> v(probs);
-    return gemm_table_upload(&t, mode, v, &arena, G);
+    return gemm_table_upload(&t, mode, v, &arena, G, side ? 1 : 0);
   }
   int upn(RowTable& t, bool bwd, std::vector<RowOp> ops) { return row_table_upload(&t, bwd, ops, &arena); }
   static RowOp nf(const Mat& x, const Mat& y) { return make_rowop(x.p, x.ld, x.gs, y.p, y.ld, y.gs, x.rows, x.cols); }
@@ -129,21 +131,21 @@ struct TD7Agent : AgentBase {
     const Mat z_cur = e_z.rows_from(0, B), z_nxt = e_z.rows_from(B, B);
     const float sigma = (float)cfg.target_policy_noise, clipv = (float)cfg.noise_clip;
     // ------------------------------------------------ encoder branch (td7.py:246-257, 299-303)
-    B200_TRY(up(E[0], kFwd, PV{fwd_problem(enc, 0, {s_all}, e_h1, kActElu)}));
-    B200_TRY(up(E[1], kFwd, PV{fwd_problem(enc, 1, {e_h1}, e_h2, kActElu)}));
-    B200_TRY(up(E[2], kFwd, PV{fwd_problem(enc, 2, {e_h2}, e_u3, kActNone)}));
+    B200_TRY(up(E[0], kFwd, PV{fwd_problem(enc, 0, {s_all}, e_h1, kActElu)}, true));
+    B200_TRY(up(E[1], kFwd, PV{fwd_problem(enc, 1, {e_h1}, e_h2, kActElu)}, true));
+    B200_TRY(up(E[2], kFwd, PV{fwd_problem(enc, 2, {e_h2}, e_u3, kActNone)}, true));
     B200_TRY(upn(En[0], false, {nf(e_u3, e_z)}));
-    B200_TRY(up(E[3], kFwd, PV{fwd_problem(enc, 3, {z_cur, act_in}, e_g1, kActElu)}));
-    B200_TRY(up(E[4], kFwd, PV{fwd_problem(enc, 4, {e_g1}, e_g2, kActElu)}));
-    B200_TRY(up(E[5], kFwd, PV{fwd_problem(enc, 5, {e_g2}, e_zsa, kActNone)}));
-    B200_TRY(up(E[6], kDgrad, PV{dgrad_problem({{&enc, 5, d_zsa, 0}}, H, d_g2, &e_g2, kActElu)}));
-    B200_TRY(up(E[7], kDgrad, PV{dgrad_problem({{&enc, 4, d_g2, 0}}, H, d_g1, &e_g1, kActElu)}));
-    B200_TRY(up(E[8], kDgrad, PV{dgrad_problem({{&enc, 3, d_g1, 0}}, Z, d_z, nullptr, 0)}));
+    B200_TRY(up(E[3], kFwd, PV{fwd_problem(enc, 3, {z_cur, act_in}, e_g1, kActElu)}, true));
+    B200_TRY(up(E[4], kFwd, PV{fwd_problem(enc, 4, {e_g1}, e_g2, kActElu)}, true));
+    B200_TRY(up(E[5], kFwd, PV{fwd_problem(enc, 5, {e_g2}, e_zsa, kActNone)}, true));
+    B200_TRY(up(E[6], kDgrad, PV{dgrad_problem({{&enc, 5, d_zsa, 0}}, H, d_g2, &e_g2, kActElu)}, true));
+    B200_TRY(up(E[7], kDgrad, PV{dgrad_problem({{&enc, 4, d_g2, 0}}, H, d_g1, &e_g1, kActElu)}, true));
+    B200_TRY(up(E[8], kDgrad, PV{dgrad_problem({{&enc, 3, d_g1, 0}}, Z, d_z, nullptr, 0)}, true));
     B200_TRY(upn(En[1], true, {nb(e_u3.rows_from(0, B), d_z, d_u3)}));
     {
       Mat h2c = e_h2.rows_from(0, B), h1c = e_h1.rows_from(0, B);
-      B200_TRY(up(E[9], kDgrad, PV{dgrad_problem({{&enc, 2, d_u3, 0}}, H, d_h2, &h2c, kActElu)}));
-      B200_TRY(up(E[10], kDgrad, PV{dgrad_problem({{&enc, 1, d_h2, 0}}, H, d_h1, &h1c, kActElu)}));
+      B200_TRY(up(E[9], kDgrad, PV{dgrad_problem({{&enc, 2, d_u3, 0}}, H, d_h2, &h2c, kActElu)}, true));
+      B200_TRY(up(E[10], kDgrad, PV{dgrad_problem({{&enc, 1, d_h2, 0}}, H, d_h1, &h1c, kActElu)}, true));
       PV w;
       wgrad_problems(w, enc, 5, d_zsa, {e_g2}, true);
       wgrad_problems(w, enc, 4, d_g2, {e_g1}, true);
@@ -151,7 +153,7 @@ struct TD7Agent : AgentBase {
       wgrad_problems(w, enc, 2, d_u3, {h2c}, true);
       wgrad_problems(w, enc, 1, d_h2, {h1c}, true);
       wgrad_problems(w, enc, 0, d_h1, {s_cur}, true);
-      B200_TRY(up(E[11], kWgrad, w));
+      B200_TRY(up(E[11], kWgrad, w, true));
     }
     // ------------------------------------------------ critic chain (td7.py:175-244, 307-315)
     // first launch: 4 x 64 tiles = one wave at 2 CTAs per SM; the policy's l0 rides with the second launch (128 tiles)
@@ -205,12 +207,12 @@ struct TD7Agent : AgentBase {
       B200_TRY(up(Wq[3], kWgrad, w0));
     }
     // ------------------------------------------------ actor step (td7.py:259-276, 319-324)
-    B200_TRY(up(Aa[0], kFwd, PV{fwd_problem(pol, 1, {pb0n, zs_f}, pp1, kActRelu)}));
-    B200_TRY(up(Aa[1], kFwd, PV{fwd_problem(pol, 2, {pp1}, pp2, kActRelu)}));
-    B200_TRY(up(Aa[2], kFwd, PV{fwd_problem(pol, 3, {pp2}, a_pi, kActTanh)}));
-    B200_TRY(up(Aa[3], kFwd, PV{fwd_problem(fe, 3, {zs_f, a_pi}, pa1, kActElu)}));
-    B200_TRY(up(Aa[4], kFwd, PV{fwd_problem(fe, 4, {pa1}, pa2, kActElu)}));
-    B200_TRY(up(Aa[5], kFwd, PV{fwd_problem(fe, 5, {pa2}, zsa_pi, kActNone)}));
+    B200_TRY(up(Aa[0], kFwd, PV{fwd_problem(pol, 1, {pb0n, zs_f}, pp1, kActRelu)}, true));
+    B200_TRY(up(Aa[1], kFwd, PV{fwd_problem(pol, 2, {pp1}, pp2, kActRelu)}, true));
+    B200_TRY(up(Aa[2], kFwd, PV{fwd_problem(pol, 3, {pp2}, a_pi, kActTanh)}, true));
+    B200_TRY(up(Aa[3], kFwd, PV{fwd_problem(fe, 3, {zs_f, a_pi}, pa1, kActElu)}, true));
+    B200_TRY(up(Aa[4], kFwd, PV{fwd_problem(fe, 4, {pa1}, pa2, kActElu)}, true));
+    B200_TRY(up(Aa[5], kFwd, PV{fwd_problem(fe, 5, {pa2}, zsa_pi, kActNone)}, true));
     B200_TRY(up(Aa[6], kFwd, PV{fwd_problem(q[0], 0, {s_cur, a_pi}, aq0[0], kActNone), fwd_problem(q[1], 0, {s_cur, a_pi}, aq0[1], kActNone)}));
     B200_TRY(upn(An[0], false, {nf(aq0[0], aq0n[0]), nf(aq0[1], aq0n[1])}));
     B200_TRY(up(Aa[7], kFwd, PV{fwd_problem(q[0], 1, {aq0n[0], zsa_pi, zs_f}, aqa[0], kActElu), fwd_problem(q[1], 1, {aq0n[1], zsa_pi, zs_f}, aqa[1], kActElu)}));
