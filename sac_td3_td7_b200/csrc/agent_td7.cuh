@@ -44,6 +44,7 @@ struct TD7Agent : AgentBase {
 
   // launch tables
   GemmTable E[16], C[24], Aa[24];
+  GemmTable We[6];         // encoder weight gradients (+Adam), one launch per layer
   GemmTable C2v[2];        // second launch of the critic chain, without / with the actor step's l0(s)
   GemmTable Wq[4], Wp[4];  // critic / policy weight gradients (+Adam), one launch per layer: [0] = last layer
   RowTable En[2], Cn[4], An[4];
@@ -146,14 +147,19 @@ struct TD7Agent : AgentBase {
       Mat h2c = e_h2.rows_from(0, B), h1c = e_h1.rows_from(0, B);
       B200_TRY(up(E[9], kDgrad, PV{dgrad_problem({{&enc, 2, d_u3, 0}}, H, d_h2, &h2c, kActElu)}, true));
       B200_TRY(up(E[10], kDgrad, PV{dgrad_problem({{&enc, 1, d_h2, 0}}, H, d_h1, &h1c, kActElu)}, true));
-      PV w;
-      wgrad_problems(w, enc, 5, d_zsa, {e_g2}, true);
-      wgrad_problems(w, enc, 4, d_g2, {e_g1}, true);
-      wgrad_problems(w, enc, 3, d_g1, {z_cur, act_in}, true);
-      wgrad_problems(w, enc, 2, d_u3, {h2c}, true);
-      wgrad_problems(w, enc, 1, d_h2, {h1c}, true);
-      wgrad_problems(w, enc, 0, d_h1, {s_cur}, true);
-      B200_TRY(up(E[11], kWgrad, w, true));
+      // one small launch per layer, issued right after the dgrad that reads that layer's weights: the encoder step runs
+      // beside the critic chain, and 64-tile launches slip into its idle SMs where one 384-tile burst would stall it
+      const Mat* dz[6] = {&d_h1, &d_h2, &d_u3, &d_g1, &d_g2, &d_zsa};
+      for (int l = 0; l < 6; ++l) {
+        PV w;
+        if (l == 0) wgrad_problems(w, enc, 0, *dz[0], {s_cur}, true);
+        else if (l == 1) wgrad_problems(w, enc, 1, *dz[1], {h1c}, true);
+        else if (l == 2) wgrad_problems(w, enc, 2, *dz[2], {h2c}, true);
+        else if (l == 3) wgrad_problems(w, enc, 3, *dz[3], {z_cur, act_in}, true);
+        else if (l == 4) wgrad_problems(w, enc, 4, *dz[4], {e_g1}, true);
+        else wgrad_problems(w, enc, 5, *dz[5], {e_g2}, true);
+        B200_TRY(up(We[l], kWgrad, w, true));
+      }
     }
     // ------------------------------------------------ critic chain (td7.py:175-244, 307-315)
     // first launch: 4 x 64 tiles = one wave at 2 CTAs per SM; the policy's l0 rides with the second launch (128 tiles)
@@ -298,7 +304,8 @@ struct TD7Agent : AgentBase {
     GL(E[3], sE); GL(E[4], sE); GL(E[5], sE);
     B200_TRY(fork.link(sP, sE));  // info slot (loss) and Adam scalars (wgrad)
     B200_TRY(launch_enc_loss(sE));
-    GL(E[6], sE); GL(E[7], sE); GL(E[8], sE); RL(En[1], sE); GL(E[9], sE); GL(E[10], sE); GL(E[11], sE);
+    GL(E[6], sE); GL(We[5], sE); GL(E[7], sE); GL(We[4], sE); GL(E[8], sE); GL(We[3], sE); RL(En[1], sE);
+    GL(E[9], sE); GL(We[2], sE); GL(E[10], sE); GL(We[1], sE); GL(We[0], sE);
     }
     // ---- critic chain
     GL(C[0], M);

@@ -404,10 +404,11 @@ __device__ __forceinline__ void store_quad(float* p, const float (&o)[4], int nv
   }
 }
 
-// MINB = CTAs per SM the register budget is sized for: 2 (<= 128 registers) for launches of more than one CTA
-// per SM, 1 (no cap: addresses and fragments stay in registers) for the small launches of a single agent.
-template <int MODE, int MINB>
-__global__ void __launch_bounds__(kGemmThreads, MINB) gemm_kernel(const __grid_constant__ FfmaLaunch L) {
+// Register budget: two CTAs per SM (<= 128 registers).  A variant without the cap was measured (fewer address
+// recomputations in the loop) and lost: a single agent's update keeps several small launches of different streams in
+// flight, and they only overlap if two CTAs fit on one SM.
+template <int MODE>
+__global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_constant__ FfmaLaunch L) {
   B200_PDL_TRIGGER();  // the setup below reads kernel parameters only: it may overlap the previous kernel
   B200_PROBE_DECL
   B200_TIMELINE(L.tag)

@@ -189,7 +189,7 @@ inline int gemm_table_launch(const GemmTable& t, int groups, cudaStream_t stream
 #ifndef B200_EMU
   static bool attr_set = false;  // > 48 KB of dynamic shared memory needs the opt-in once per kernel
   if (!attr_set) {
-    void (*ks[6])(FfmaLaunch) = {gemm_kernel<kFwd, 1>, gemm_kernel<kDgrad, 1>, gemm_kernel<kWgrad, 1>, gemm_kernel<kFwd, 2>, gemm_kernel<kDgrad, 2>, gemm_kernel<kWgrad, 2>};
+    void (*ks[3])(FfmaLaunch) = {gemm_kernel<kFwd>, gemm_kernel<kDgrad>, gemm_kernel<kWgrad>};
     for (auto k : ks) B200_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(kMaxSplitK)));
     B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kFwd>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
     B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kDgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
@@ -210,11 +210,7 @@ inline int gemm_table_launch(const GemmTable& t, int groups, cudaStream_t stream
     const int sk = t.launch.splitk;
     dim3 grid((unsigned)(t.total_tiles * sk), (unsigned)groups, 1), block(kGemmThreads, 1, 1);
     const size_t smem = (size_t)gemm_smem_bytes(sk);
-    // one CTA per SM or fewer: the variant compiled without the 128-register cap
-    static const int fat_max = [] { const char* e = getenv("B200RL_FAT_MAX_CTAS"); return e ? atoi(e) : 148; }();
-    const bool fat = (long long)t.total_tiles * sk * groups <= fat_max;
-    void (*k)(FfmaLaunch) = fat ? (t.mode == kFwd ? gemm_kernel<kFwd, 1> : t.mode == kDgrad ? gemm_kernel<kDgrad, 1> : gemm_kernel<kWgrad, 1>)
-                                : (t.mode == kFwd ? gemm_kernel<kFwd, 2> : t.mode == kDgrad ? gemm_kernel<kDgrad, 2> : gemm_kernel<kWgrad, 2>);
+    void (*k)(FfmaLaunch) = t.mode == kFwd ? gemm_kernel<kFwd> : t.mode == kDgrad ? gemm_kernel<kDgrad> : gemm_kernel<kWgrad>;
 #ifndef B200_EMU
     if (sk > 1) {
       ++launch_counter();
