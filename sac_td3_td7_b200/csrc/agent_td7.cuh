@@ -341,10 +341,12 @@ struct TD7Agent : AgentBase {
     GL(C[15], M);
     B200_TRY(fork.link(M, sN)); GL(Wq[2], sN);
     RL(critic_norm_bwd, M); GL(Wq[3], M);
-    B200_TRY(fork.link(sN, M));
+    if (!actor) B200_TRY(fork.link(sN, M));
     if (actor) {
       B200_TRY(fork.link(sA, M));
-      GL(Aa[6], M); RL(An[0], M); GL(Aa[7], M); GL(Aa[8], M);
+      GL(Aa[6], M); RL(An[0], M);   // q01 was just updated on this stream; the deeper critic layers are still being
+      B200_TRY(fork.link(sN, M));   // updated on sN: joined only where the new q1 weights are first read
+      GL(Aa[7], M); GL(Aa[8], M);
       B200_TRY(fork.link(M, sN));
       GL(Aa[9], sN);
       B200_TRY(launch_actor_loss(sN));
