@@ -17,16 +17,26 @@
 // applies Adam in place (torch.optim.Adam single-tensor ordering), so gradients never
 // round-trip through HBM in the stacked-seed case.
 //
-// Tiling: CTA = 256 threads, 32x32 output tile, 32-deep reduction chunks in a 3-stage
-// cp.async (LDGSTS) pipeline: every thread issues one 16-byte copy per operand per chunk
+// Tiling: CTA = 256 threads, 32x32 output tile, 64-deep reduction chunks in a 3-stage
+// cp.async (LDGSTS) pipeline: every thread issues two 16-byte copies per operand per chunk
 // straight from global/L2 into shared memory (no register staging, no transposition), two
-// chunks ahead of the math.  The eight warps split each chunk's reduction (4 r's each) and
-// every lane owns a 4x8 register tile (128 FFMA per 12 LDS.128); the eight partial tiles
-// are summed in a fixed order through shared memory, so results are bit-reproducible run
-// to run.  Operands that are contiguous along the reduction in global memory keep that
-// orientation in shared memory, XOR-swizzled at float4 granularity so the strided float4
-// reads are bank-conflict free; ragged / unaligned strips (obs and action widths such as
-// 17, 6, 23) take a zero-filling register path.
+// chunks ahead of the math.  The eight warps split each chunk's reduction (8 r's each) and
+// every lane owns a 4x8 register tile (128 FFMA per 12 LDS.128; dgrad / wgrad pair
+// neighbouring columns into FFMA2); the eight partial tiles are summed in a fixed order
+// through shared memory, so results are bit-reproducible run to run.  Operands that are
+// contiguous along the reduction in global memory keep that orientation in shared memory,
+// XOR-swizzled at float4 granularity so the strided float4 reads are bank-conflict free;
+// ragged / unaligned strips (obs and action widths such as 17, 6, 23) take an out-of-line
+// zero-filling path.
+//
+// A single agent's layer is only 64 tiles of 4-12 serial chunks, so launches that would
+// leave more than half of the 148 SMs idle run as thread-block CLUSTERS of 2 or 4 CTAs per
+// tile: each CTA reduces a contiguous slice of the chunks, the non-leaders push their partial
+// tile into the leader's shared memory (DSMEM) and the leader adds them in rank order and runs
+// the epilogue -- deterministic, no global scratch, no atomics.  The epilogue's operands (bias,
+// saved activations, Adam moments and scalars) are requested before the cross-warp reduction so
+// that their L2 round trips overlap it.  Measured per launch on B200 (profiles/probe_phases.py):
+// ~1.2 us between dependent launches, ~0.4 us setup, ~0.6 us per chunk, ~0.35 us reduction.
 //
 // Why FFMA and not tcgen05 here: a single agent's layer is 256x256x(<=768) -- 64 tiles --
 // and parity is fp32 at 1e-5 (BASELINE.json north_star), which single-pass TF32/BF16

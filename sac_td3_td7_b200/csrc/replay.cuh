@@ -337,9 +337,21 @@ __global__ void lap_append_priority_kernel(float* __restrict__ priority, const f
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) priority[(pos + i) % cap] = *max_priority;
 }
-// the per-environment-step form (a handful of rows): one CTA writes the priorities and repairs the sum tree
-__global__ void __launch_bounds__(1024) lap_append_fix_kernel(float* __restrict__ priority, const float* __restrict__ max_priority, FixArgs fix) {
+// the per-environment-step form (a handful of rows): one CTA copies the rows -- `src` may be device memory or pinned
+// host memory read over the bus, so the step needs no separate H2D copy -- writes the priorities and repairs the sum
+// tree.  src == null: rows were copied by the caller; priority == null: uniform buffer.
+__global__ void __launch_bounds__(1024) lap_append_fix_kernel(const float* __restrict__ src, float* __restrict__ dst_base, int row_stride,
+                                                              float* __restrict__ priority, const float* __restrict__ max_priority, FixArgs fix) {
   B200_PDL_PROLOGUE();
+  if (src) {
+    const int q4 = row_stride >> 2;  // float4 per row
+    for (int i = threadIdx.x; i < fix.n * q4; i += blockDim.x) {
+      const int r = i / q4, c = i - r * q4;
+      const float4 v = *reinterpret_cast<const float4*>(src + (long long)r * row_stride + c * 4);
+      *reinterpret_cast<float4*>(dst_base + ((fix.pos + r) % fix.cap) * row_stride + c * 4) = v;
+    }
+  }
+  if (!priority) return;
   const float m = *max_priority;
   for (int i = threadIdx.x; i < fix.n; i += blockDim.x) priority[(fix.pos + i) % fix.cap] = m;
   __threadfence_block();
@@ -404,19 +416,40 @@ struct Replay {
     B200_REQUIRE(count >= 0 && count <= capacity, "replay.append: count must be within capacity");
     if (count == 0) return kOk;
     const long long pos = ptr[g];
-    if (!(share_rows && g > 0)) {
-      float* dst_base = d_rows + (share_rows ? 0 : (long long)g * capacity * row_stride);
+    const bool want_rows = !(share_rows && g > 0);
+    float* dst_base = d_rows + (share_rows ? 0 : (long long)g * capacity * row_stride);
+    // small appends (the per-step case) whose source the GPU can read directly -- device memory, or pinned / registered
+    // host memory -- are ONE kernel: row copy + priorities + tree repair
+    const float* direct = nullptr;
+#ifndef B200_EMU
+    if (want_rows && count <= 64 && (reinterpret_cast<uintptr_t>(rows) & 15) == 0 && (!prioritized || sums_valid)) {
+      if (kind == cudaMemcpyDeviceToDevice) {
+        direct = rows;
+      } else {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, rows) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) direct = static_cast<const float*>(at.devicePointer);
+        (void)cudaGetLastError();
+      }
+    }
+#endif
+    if (want_rows && !direct) {
       const long long first = std::min(count, capacity - pos);
       B200_CHECK_CUDA(cudaMemcpyAsync(dst_base + pos * row_stride, rows, (size_t)first * row_stride * sizeof(float), kind, stream));
       if (first < count)
         B200_CHECK_CUDA(cudaMemcpyAsync(dst_base, rows + first * row_stride, (size_t)(count - first) * row_stride * sizeof(float), kind, stream));
     }
-    if (prioritized) {
-      if (count <= 4096 && sums_valid) {
-        FixArgs f = fix_args(nullptr, 0, (int)count);
-        f.priority += (long long)g * cap_pad; f.tile_sums += (long long)g * max_tiles; f.super_sums += (long long)g * max_supers;
+    if (prioritized || direct) {
+      if (count <= 4096 && (sums_valid || !prioritized)) {
+        FixArgs f;
+        memset(&f, 0, sizeof(f));
+        if (prioritized) {
+          f = fix_args(nullptr, 0, (int)count);
+          f.priority += (long long)g * cap_pad; f.tile_sums += (long long)g * max_tiles; f.super_sums += (long long)g * max_supers;
+        }
+        f.n = (int)count; f.cap = capacity;
         f.pos = pos;
-        B200_LAUNCH(lap_append_fix_kernel, dim3(1), dim3(count <= 32 ? 64 : 1024), 0, stream, d_priority + (long long)g * cap_pad, d_max_priority + g, f);
+        B200_LAUNCH(lap_append_fix_kernel, dim3(1), dim3(count <= 32 ? 64 : 1024), 0, stream, direct, dst_base, row_stride,
+                    prioritized ? d_priority + (long long)g * cap_pad : nullptr, d_max_priority + g, f);
       } else {
         dim3 grid((unsigned)ceil_div((int)count, 256)), block(256);
         B200_LAUNCH(lap_append_priority_kernel, grid, block, 0, stream, d_priority + (long long)g * cap_pad, d_max_priority + g, pos, (int)count, capacity);

@@ -1,2 +1,2 @@
-timeout 600 python -m pytest tests/test_agent_parity.py tests/test_dropin_gpu.py -x -q -m gpu 2>&1 | tail -2
-timeout 300 python bench.py --steps 3000 --warmup 200 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-200
+timeout 600 python -m pytest tests/test_dropin_gpu.py tests/test_replay_kernels.py -x -q -m gpu 2>&1 | tail -5
+timeout 300 python profiles/e2e_prof.py 2>&1 | tail -3

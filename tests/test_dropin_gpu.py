@@ -183,6 +183,34 @@ def test_zero_copy_sample_hand_off():
     assert b1.sample(256) is other._inbox
 
 
+def test_single_kernel_append_from_pinned_and_device_rows():
+    """Per-step appends whose source the GPU can read (pinned host memory, device memory) are one kernel (row copy +
+    priorities + tree repair); the result must be what the staged path (pageable numpy rows) produces, across the wrap."""
+    from sac_td3_td7_b200.rl.replay_memory import LAPReplayMemory, SimpleReplayMemory
+
+    for cls in (LAPReplayMemory, SimpleReplayMemory):
+        bufs = [cls(300, "Hopper-v4") for _ in range(3)]
+        g = np.random.default_rng(9)
+        stride = bufs[0].row_stride
+        pinned = torch.empty((8, stride), dtype=torch.float32).pin_memory()
+        for it in range(120):  # 120 x 3 rows: wraps the 300-row ring
+            rows = g.standard_normal((3, stride)).astype(np.float32)
+            slot = pinned[(it % 2) * 4:(it % 2) * 4 + 3]
+            torch.cuda.synchronize()
+            slot.copy_(torch.from_numpy(rows))
+            bufs[0].append_rows(rows)                       # pageable: cudaMemcpyAsync + kernel
+            bufs[1].append_rows(slot.numpy())               # pinned: one kernel reading host memory
+            bufs[2].append_rows(torch.from_numpy(rows).cuda())  # device rows: one kernel
+        u = torch.rand(64)
+        ref = bufs[0].sample(64, u=u)
+        for b in bufs[1:]:
+            got = b.sample(64, u=u)
+            assert (b.ptr, b.size) == (bufs[0].ptr, bufs[0].size)
+            assert np.array_equal(b.ind, bufs[0].ind)
+            for k in ref:
+                assert torch.equal(got[k], ref[k]), k
+
+
 def test_no_cpu_fallback_paths():
     from sac_td3_td7_b200 import _lib
     from sac_td3_td7_b200.rl import nn as bnn
