@@ -317,7 +317,8 @@ def run_gpu_arm(args):
     g_flops, g_ms = gemm_roofline(lib, torch, S, A)
     ach_tf = g_flops / (g_ms * 1e-3) / 1e12
     roofline = {"kernel": "gemm_kernel<fwd> (grouped FFMA GEMM, 5 independent layers of the TD7 critic chain, 320 CTAs)", "bound": "tensor",
-                "achieved": ach_tf, "peak": bf16_burst, "unit": "TFLOP/s", "frac": ach_tf / bf16_burst, "traffic": None,
+                "achieved": ach_tf, "peak": bf16_burst, "unit": "TFLOP/s", "frac": ach_tf / bf16_burst,
+                "traffic": 2.7392e6,  # dram__bytes_read + write of this launch, profiles/gemm_ffma_ncu_full_r01.summary.txt (operands are L2-resident)
                 "peak_source": peak_src + ", dense bf16 cuBLAS burst",
                 "note": "fp32 FFMA by design (1e-5 fp32 parity rules out single-pass TF32/BF16); the non-tensor fp32 peak of a B200 is ~74.5 TFLOP/s",
                 "fp32_ffma_peak_tflops": 74.5, "frac_of_fp32_ffma_peak": ach_tf / 74.5, "launch_ms": g_ms, "flops_per_launch": g_flops}
