@@ -164,6 +164,29 @@ class Agent(ABC):
         _lib.check(self._lib.b200rl_agent_read_info(self._h, first_step, count, seed, buf.ctypes.data, _stream()))
         return buf
 
+    def info_dicts(self, first_step: int, count: int, seed: int = 0) -> list[dict]:
+        """The info dicts train_ops returned for updates first_step .. first_step+count-1 of stacked seed `seed`, as plain
+        floats (None where the reference returns None), from ONE read of the engine's info ring -- what an episode-end
+        ``log_train_infos`` (run.py:53-84) needs after a ``train_ops_n`` burst."""
+        rows = self.read_infos(first_step, count, seed)
+        out = []
+        sync, self.sync_info = getattr(self, "sync_info", False), False
+        try:
+            for i in range(count):
+                step = first_step + i
+                d = self._info_dict(step, self._actor_step(step))
+                out.append({k: (None if v is None else float(rows[i][v._col])) for k, v in d.items()})
+        finally:
+            self.sync_info = sync
+        return out
+
+    def export_to(self, reference_agent) -> None:
+        """Copy the current networks into an agent of the REFERENCE's classes (same attribute names, same
+        ``state_dict`` keys), e.g. so that ``rl/replayer.py:43-45`` can render a policy trained here."""
+        self._pull()
+        for attr, _ in self.NETS:
+            getattr(reference_agent, attr).load_state_dict(getattr(self, attr).state_dict())
+
     def seed_population(self, base_seed: int) -> None:
         """Give every stacked seed its own initial networks: seed g is built exactly like a fresh
         single agent under ``torch.manual_seed(base_seed + g)`` (the reference runs seeds as separate

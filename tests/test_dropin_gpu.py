@@ -211,6 +211,40 @@ def test_single_kernel_append_from_pinned_and_device_rows():
                 assert torch.equal(got[k], ref[k]), k
 
 
+def test_info_dicts_after_a_burst_and_export_to_reference_classes():
+    """ info_dicts() = the dicts train_ops would have returned, from one ring read; export_to()
+    fills an agent of the reference's classes (here: a stand-in with the same attribute / state_dict layout, the real
+    classes cannot travel to the GPU box) so that the oracle forward of the exported weights equals agent.sample()."""
+    from oracle import nets as onets
+    from sac_td3_td7_b200.rl import nn as bnn
+    from sac_td3_td7_b200.rl.agent import TD7
+
+    agent, buf, algo, _ = _mk("td7_halfcheetah_lap")
+    per_call = [agent.train_ops(buf.sample(gu.BATCH), replay_buffer=buf) for _ in range(3)]
+    burst = agent.train_ops_n(5, buf)
+    dicts = agent.info_dicts(1, 8)
+    assert [d["train/policy"] is None for d in dicts] == [(k + 1) % 2 != 0 for k in range(8)]
+    for d, ref in zip(dicts, per_call + burst):
+        for k, v in ref.items():
+            assert (d[k] is None) == (v is None) and (v is None or d[k] == float(v))
+
+    class RefAgent:  # attribute names and module classes of rl/agent/td7.py:53-66
+        def __init__(self, S, A):
+            self.policy, self.q1, self.q2 = bnn.SALEActor(S, A), bnn.SALECritic(S, A), bnn.SALECritic(S, A)
+            self.encoder, self.fixed_encoder, self.fixed_encoder_target = bnn.SALEEncoder(S, A), bnn.SALEEncoder(S, A), bnn.SALEEncoder(S, A)
+            self.target_q1, self.target_q2 = bnn.SALECritic(S, A), bnn.SALECritic(S, A)
+            self.target_policy = self.policy
+
+    ref = RefAgent(agent.state_dim, agent.action_dim)
+    agent.export_to(ref)
+    obs = np.linspace(-1, 1, agent.state_dim).astype(np.float32)
+    cpu = lambda m: {k: v.detach().cpu() for k, v in m.state_dict().items()}  # noqa: E731
+    s = torch.tensor(obs)[None]
+    a = onets.sale_actor(cpu(ref.policy), s, onets.encode_state(cpu(ref.fixed_encoder), s))[0].numpy()
+    assert np.abs(agent.sample(obs, True) - (a * agent.action_scale + agent.action_bias)).max() < 1e-5
+    assert torch.equal(ref.q1.q2.weight, agent.q1.q2.weight.cpu()) and torch.equal(ref.encoder.zs1.weight, agent.encoder.zs1.weight.cpu())
+
+
 def test_no_cpu_fallback_paths():
     from sac_td3_td7_b200 import _lib
     from sac_td3_td7_b200.rl import nn as bnn
