@@ -299,14 +299,12 @@ struct TD7Agent : AgentBase {
     B200_TRY(launch_gauss(noise, 0, sP));
     // ---- encoder branch
     B200_TRY(fork.link(M, sE));
-    if (getenv("B200RL_DEBUG_SKIP_ENCODER") == nullptr) {  // (measurement knob: how much does the side branch cost the critical chain?)
     GL(E[0], sE); GL(E[1], sE); GL(E[2], sE); RL(En[0], sE);
     GL(E[3], sE); GL(E[4], sE); GL(E[5], sE);
     B200_TRY(fork.link(sP, sE));  // info slot (loss) and Adam scalars (wgrad)
     B200_TRY(launch_enc_loss(sE));
     GL(E[6], sE); GL(We[5], sE); GL(E[7], sE); GL(We[4], sE); GL(E[8], sE); GL(We[3], sE); RL(En[1], sE);
     GL(E[9], sE); GL(We[2], sE); GL(E[10], sE); GL(We[1], sE); GL(We[0], sE);
-    }
     // ---- critic chain
     GL(C[0], M);
     B200_TRY(fork.link(M, sN));
