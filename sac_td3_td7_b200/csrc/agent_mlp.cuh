@@ -26,8 +26,10 @@ struct MlpAgent : AgentBase {
   int Aout = 0;
   Net pol, q[2], qt[2];
   float *la_p = nullptr, *la_m = nullptr, *la_v = nullptr, *la_g = nullptr;  // SAC log-temperature [G]
-  TensorSlice* d_slices = nullptr;
-  int nslices = 0;
+  NormChunk* d_chunks = nullptr;  // the policy's gradient tensors, cut into chunks (norm/policy)
+  double* d_norm_partial = nullptr;
+  unsigned* d_norm_counter = nullptr;
+  int nchunks = 0, nslices = 0;
 
   Mat noise, noise2;
   Mat h1, h2, pout_n, a_next, logp_n, c1[2], c2[2], qv[2], tc1[2], tc2[2], qtv[2], dq[2], d_c2[2], d_c1[2];
@@ -83,8 +85,14 @@ struct MlpAgent : AgentBase {
         sl.push_back(TensorSlice{d.b_off, (long long)d.out});
       }
       nslices = (int)sl.size();
-      B200_TRY(arena.alloc(&d_slices, sl.size()));
-      B200_CHECK_CUDA(cudaMemcpy(d_slices, sl.data(), sl.size() * sizeof(TensorSlice), cudaMemcpyHostToDevice));
+      std::vector<NormChunk> ch;
+      for (int t = 0; t < nslices; ++t)
+        for (long long o = 0; o < sl[t].numel; o += kNormChunk) ch.push_back(NormChunk{sl[t].offset + o, (int)std::min<long long>(kNormChunk, sl[t].numel - o), t});
+      nchunks = (int)ch.size();
+      B200_TRY(arena.alloc(&d_chunks, ch.size()));
+      B200_CHECK_CUDA(cudaMemcpy(d_chunks, ch.data(), ch.size() * sizeof(NormChunk), cudaMemcpyHostToDevice));
+      B200_TRY(arena.alloc(&d_norm_partial, (size_t)G * nchunks));
+      B200_TRY(arena.alloc(&d_norm_counter, (size_t)G));
     }
     layout_acts();
     act_stride = act_cursor;
@@ -254,7 +262,8 @@ struct MlpAgent : AgentBase {
       GL(Up[0], M); GL(Up[1], M); GL(Uw, M);
       if (!sac) {
         B200_TRY(fork.link(M, sN));
-        B200_LAUNCH(grad_norm_sum_kernel, dim3((unsigned)G), dim3(256), 0, sN, pol.grad, pol.gs, d_slices, nslices, d_info, info_cols, 2,
+        B200_LAUNCH(grad_norm_sum_kernel, dim3((unsigned)nchunks, (unsigned)G), dim3(256), 0, sN, pol.grad, pol.gs, d_chunks, nchunks, nslices, d_norm_partial, d_norm_counter,
+                    d_info, info_cols, 2,
                     (long long)kInfoRing * info_cols, d_step);
         B200_CHECK_LAUNCH();
         B200_TRY(fork.link(sN, M));

@@ -136,32 +136,51 @@ __global__ void __launch_bounds__(256) fill_kernel(float* __restrict__ p, long l
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
 
-// sum over tensors of ||grad||_2 (rl/nn/utils.py:13-19): one block per tensor slice table entry
+// sum over tensors of ||grad||_2 (rl/nn/utils.py:13-19).  The tensors are cut into chunks of kNormChunk elements; one
+// CTA reduces one chunk (fp64 sum of squares, fixed order), and the CTA that finishes last adds the chunk partials of
+// every tensor in chunk order, takes the square roots and writes the total -- deterministic, and a few microseconds
+// instead of one CTA walking 70k+ elements at one L2 round trip per pass.
 struct TensorSlice { long long offset; long long numel; };
-__global__ void __launch_bounds__(256) grad_norm_sum_kernel(const float* __restrict__ grad_base, long long grad_gs, const TensorSlice* __restrict__ slices, int nslices,
-                                                            float* __restrict__ info, int info_stride, int info_col, long long info_gs, const StepState* st) {
+struct NormChunk { long long offset; int count; int slice; };
+constexpr int kNormChunk = 4096;
+__global__ void __launch_bounds__(256) grad_norm_sum_kernel(const float* __restrict__ grad_base, long long grad_gs, const NormChunk* __restrict__ chunks, int nchunks,
+                                                            int nslices, double* __restrict__ partial, unsigned* __restrict__ counter, float* __restrict__ info,
+                                                            int info_stride, int info_col, long long info_gs, const StepState* st) {
   B200_PDL_PROLOGUE();
   __shared__ double red[8];
-  __shared__ double total;
-  const int g = blockIdx.x;
-  const float* grad = grad_base + (long long)g * grad_gs;
-  if (threadIdx.x == 0) total = 0.0;
-  __syncthreads();
-  for (int t = 0; t < nslices; ++t) {
-    const float* gp = grad + slices[t].offset;
-    double s = 0.0;
-    for (long long i = threadIdx.x; i < slices[t].numel; i += blockDim.x) { double x = gp[i]; s += x * x; }
-    s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double a = 0.0;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += red[w];
-      total += (double)sqrtf((float)a);
-    }
-    __syncthreads();
+  __shared__ bool is_last;
+  const int g = blockIdx.y, c = blockIdx.x;
+  const NormChunk ch = chunks[c];
+  const float* gp = grad_base + (long long)g * grad_gs + ch.offset;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < ch.count; i += blockDim.x) {
+    const double x = gp[i];
+    s += x * x;
   }
-  if (threadIdx.x == 0) info[g * info_gs + (long long)st->info_slot * info_stride + info_col] = (float)total;
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    for (int w = 0; w < 8; ++w) a += red[w];
+    partial[(long long)g * nchunks + c] = a;
+    __threadfence();
+    is_last = atomicAdd(&counter[g], 1u) == (unsigned)(nchunks - 1);
+  }
+  __syncthreads();
+  if (!is_last || threadIdx.x != 0) return;
+  __threadfence();
+  const volatile double* pp = partial + (long long)g * nchunks;
+  double total = 0.0, acc = 0.0;
+  int cur = 0;
+  for (int k = 0; k < nchunks; ++k) {  // chunks are stored slice by slice
+    if (chunks[k].slice != cur) { total += (double)sqrtf((float)acc); acc = 0.0; cur = chunks[k].slice; }
+    acc += pp[k];
+  }
+  total += (double)sqrtf((float)acc);
+  (void)nslices;
+  info[g * info_gs + (long long)st->info_slot * info_stride + info_col] = (float)total;
+  counter[g] = 0u;  // ready for the next replay of the graph
 }
 
 // ----------------------------------------------------------------------------- block reductions (fixed order)

@@ -1,1 +1,3 @@
-timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_replay_kernels.py tests/test_op_kernels.py -x -q -m gpu > gpurun_out/memcheck.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/memcheck.log; grep -c "Invalid\|ERROR SUMMARY" gpurun_out/memcheck.log; grep "ERROR SUMMARY" gpurun_out/memcheck.log | tail -3
+timeout 600 python -m pytest tests/test_agent_parity.py tests/test_dropin_gpu.py -x -q -m gpu 2>&1 | tail -2
+timeout 300 python bench.py --workload td3_hopper_1M --steps 3000 --warmup 200 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-200
+timeout 300 python bench.py --workload sac_walker2d_1M --steps 3000 --warmup 200 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-200
