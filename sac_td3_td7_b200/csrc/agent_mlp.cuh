@@ -36,7 +36,7 @@ struct MlpAgent : AgentBase {
   Mat g1, g2, pout, a_pi, logp, ac1[2], ac2[2], qpi[2], dqa[2], dlogp, d_ac2[2], d_ac1[2], d_api, d_pout, d_g2, d_g1;
   Mat y_dbg, prio_dbg;
 
-  GemmTable T[2][3], Tq[3], Td[2], Tw, U[3], Ud[3], Up[2], Uw;
+  GemmTable T[2][3], Tq[3], Td[2], TwL[3], U[3], Ud[3], Up[2], UwL[3];  // TwL / UwL: critic / policy weight gradients (+Adam) per layer
 
   void layout_acts() {
     act_cursor = 0;
@@ -135,13 +135,15 @@ struct MlpAgent : AgentBase {
     B200_TRY(up(Td[0], kDgrad, PV{dgrad_problem({{&q[0], 2, dq[0], 0}}, H, d_c2[0], &c2[0], kActRelu), dgrad_problem({{&q[1], 2, dq[1], 0}}, H, d_c2[1], &c2[1], kActRelu)}));
     B200_TRY(up(Td[1], kDgrad, PV{dgrad_problem({{&q[0], 1, d_c2[0], 0}}, H, d_c1[0], &c1[0], kActRelu), dgrad_problem({{&q[1], 1, d_c2[1], 0}}, H, d_c1[1], &c1[1], kActRelu)}));
     {
-      PV w;
+      // one launch per layer: layer l's gradient (and its in-place Adam step) starts as soon as the dgrad that READS layer
+      // l's weights has finished
+      PV w2, w1, w0;
       for (int k = 0; k < 2; ++k) {
-        wgrad_problems(w, q[k], 2, dq[k], {c2[k]}, true);
-        wgrad_problems(w, q[k], 1, d_c2[k], {c1[k]}, true);
-        wgrad_problems(w, q[k], 0, d_c1[k], {s_cur, act_in}, true);
+        wgrad_problems(w2, q[k], 2, dq[k], {c2[k]}, true);
+        wgrad_problems(w1, q[k], 1, d_c2[k], {c1[k]}, true);
+        wgrad_problems(w0, q[k], 0, d_c1[k], {s_cur, act_in}, true);
       }
-      B200_TRY(up(Tw, kWgrad, w));
+      B200_TRY(up(TwL[2], kWgrad, w2)); B200_TRY(up(TwL[1], kWgrad, w1)); B200_TRY(up(TwL[0], kWgrad, w0));
     }
     B200_TRY(up(U[0], kFwd, PV{fwd_problem(q[0], 0, {s_cur, a_pi}, ac1[0], kActRelu), fwd_problem(q[1], 0, {s_cur, a_pi}, ac1[1], kActRelu)}));
     B200_TRY(up(U[1], kFwd, PV{fwd_problem(q[0], 1, {ac1[0]}, ac2[0], kActRelu), fwd_problem(q[1], 1, {ac1[1]}, ac2[1], kActRelu)}));
@@ -154,11 +156,11 @@ struct MlpAgent : AgentBase {
     B200_TRY(up(Up[0], kDgrad, PV{dgrad_problem({{&pol, 2, d_last, 0}}, H, d_g2, &g2, kActRelu)}));
     B200_TRY(up(Up[1], kDgrad, PV{dgrad_problem({{&pol, 1, d_g2, 0}}, H, d_g1, &g1, kActRelu)}));
     {
-      PV w;
-      wgrad_problems(w, pol, 2, d_last, {g2}, true);
-      wgrad_problems(w, pol, 1, d_g2, {g1}, true);
-      wgrad_problems(w, pol, 0, d_g1, {s_cur}, true);
-      B200_TRY(up(Uw, kWgrad, w));
+      PV w2, w1, w0;
+      wgrad_problems(w2, pol, 2, d_last, {g2}, true);
+      wgrad_problems(w1, pol, 1, d_g2, {g1}, true);
+      wgrad_problems(w0, pol, 0, d_g1, {s_cur}, true);
+      B200_TRY(up(UwL[2], kWgrad, w2)); B200_TRY(up(UwL[1], kWgrad, w1)); B200_TRY(up(UwL[0], kWgrad, w0));
     }
     built = true;
     return kOk;
@@ -247,7 +249,21 @@ struct MlpAgent : AgentBase {
       B200_TRY(fork.link(M, sP));
       B200_TRY(bound->scatter_and_fix(prio_dbg.p, act_stride, B, sP));
     }
-    GL(Td[0], M); GL(Td[1], M); GL(Tw, M);
+    cudaStream_t sQ = fork.side[1], sW = fork.side[2];
+    GL(Td[0], M);
+    B200_TRY(fork.link(M, sW)); GL(TwL[2], sW);  // layer-2 weights were last read by Td[0]
+    GL(Td[1], M);
+    B200_TRY(fork.link(M, sW)); GL(TwL[1], sW);
+    GL(TwL[0], M);
+    B200_TRY(fork.link(sW, M));
+    // td3.py:239 / sac.py:293 -- target critics <- Polyak(critics): TD3 only on actor steps, SAC every call.  The critics
+    // are final here, so the two target updates leave the chain and run beside the actor step.
+    const bool polyak_now = sac || actor;
+    if (polyak_now) {
+      B200_TRY(fork.link(M, sQ));
+      B200_TRY(launch_polyak(qt[0], q[0], sQ));
+      B200_TRY(launch_polyak(qt[1], q[1], sQ));
+    }
     if (sac) B200_TRY(fork.link(sN, M));
     if (actor) {
       GL(U[0], M); GL(U[1], M); GL(U[2], M);
@@ -259,7 +275,12 @@ struct MlpAgent : AgentBase {
                     (float)cfg.min_log_std, (float)cfg.max_log_std, act_stride, act_stride, act_stride, act_stride);
         B200_CHECK_LAUNCH();
       }
-      GL(Up[0], M); GL(Up[1], M); GL(Uw, M);
+      GL(Up[0], M);
+      B200_TRY(fork.link(M, sW)); GL(UwL[2], sW);  // layer-2 weights were last read by Up[0]
+      GL(Up[1], M);
+      B200_TRY(fork.link(M, sW)); GL(UwL[1], sW);
+      GL(UwL[0], M);
+      B200_TRY(fork.link(sW, M));
       if (!sac) {
         B200_TRY(fork.link(M, sN));
         B200_LAUNCH(grad_norm_sum_kernel, dim3((unsigned)nchunks, (unsigned)G), dim3(256), 0, sN, pol.grad, pol.gs, d_chunks, nchunks, nslices, d_norm_partial, d_norm_counter,
@@ -273,10 +294,9 @@ struct MlpAgent : AgentBase {
         B200_CHECK_LAUNCH();
       }
     }
-    if (sac || actor) {  // td3.py:239 / sac.py:293: TD3 only on actor steps, SAC every call
-      B200_TRY(launch_polyak(qt[0], q[0], M));
-      B200_TRY(launch_polyak(qt[1], q[1], M));
-      if (!sac) B200_TRY(launch_polyak(pol, pol, M));  // target_policy aliases policy (td3.py:86)
+    if (polyak_now) {
+      if (!sac) B200_TRY(launch_polyak(pol, pol, M));  // target_policy aliases policy (td3.py:86): after its Adam step
+      B200_TRY(fork.link(sQ, M));
     }
     if (fix_tree) B200_TRY(fork.link(sP, M));
     return kOk;
