@@ -2,7 +2,7 @@
 157,180-181), restated here line by line for the check (host logic only; no GPU)."""
 import numpy as np
 
-from sac_td3_td7_b200.runlog import PopulationLogger, RunLogger, mean_with_dirty_eles, test_info_from_returns as summarize_returns
+from sac_td3_td7_b200.runlog import PopulationLogger, RunLogger, mean_with_dirty_eles, summarize_returns
 
 
 def reference_train_lines(episodes):
