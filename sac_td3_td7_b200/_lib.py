@@ -161,3 +161,24 @@ def check(status: int, cdll: C.CDLL | None = None) -> None:
     if status != 0:
         msg = (cdll or lib()).b200rl_last_error()
         raise B200RLError(f"b200rl error {status}: {msg.decode() if msg else '?'}")
+
+
+_raw_stream = None
+
+
+def current_stream_ptr() -> int:
+    """``cudaStream_t`` of torch's current stream on the current device, as an int.
+
+    ``torch.cuda.current_stream().cuda_stream`` costs ~3 us per call (device-index resolution, availability checks,
+    a Stream object); the per-step API makes four such calls per update, so the raw binding is used when present."""
+    global _raw_stream
+    if _raw_stream is None:
+        import torch
+
+        raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+        if raw is not None:
+            get_dev = torch._C._cuda_getDevice
+            _raw_stream = lambda: raw(get_dev())  # noqa: E731
+        else:
+            _raw_stream = lambda: torch.cuda.current_stream().cuda_stream  # noqa: E731
+    return _raw_stream()

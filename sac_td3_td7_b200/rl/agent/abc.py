@@ -20,8 +20,7 @@ from ... import _lib
 AGENT = TypeVar("AGENT", bound="Agent")
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+_stream = _lib.current_stream_ptr
 
 
 class LazyScalar:

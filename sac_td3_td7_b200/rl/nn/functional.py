@@ -12,8 +12,7 @@ from ... import _lib
 ACT = {None: 0, "none": 0, "relu": 1, "elu": 2, "tanh": 3}
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+_stream = _lib.current_stream_ptr
 
 
 def _chk(t: torch.Tensor) -> torch.Tensor:

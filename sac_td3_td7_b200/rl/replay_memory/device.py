@@ -21,8 +21,7 @@ from ...envs import resolve
 from .base import BaseReplayMemory
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+_stream = _lib.current_stream_ptr
 
 
 class _DeviceRing(BaseReplayMemory):
