@@ -245,6 +245,40 @@ def test_info_dicts_after_a_burst_and_export_to_reference_classes():
     assert torch.equal(ref.q1.q2.weight, agent.q1.q2.weight.cpu()) and torch.equal(ref.encoder.zs1.weight, agent.encoder.zs1.weight.cpu())
 
 
+def test_sum_tree_stays_exact_over_a_long_run():
+    """600 TD7 updates (two hard updates with reset_max_priority, appends wrapping the ring in between): the sampler's
+    incrementally repaired sum tree must give the same indices as a tree rebuilt from the priorities, and as
+    torch.cumsum + searchsorted on the priorities read back (the reference's sampler, lap.py:45-54)."""
+    from sac_td3_td7_b200 import _lib
+    from sac_td3_td7_b200.rl.agent import TD7
+    from sac_td3_td7_b200.rl.replay_memory import LAPReplayMemory
+
+    torch.manual_seed(11)
+    env, cap = "Hopper-v4", 20_000
+    agent, buf = TD7(env, use_lap=True), LAPReplayMemory(cap, env)
+    buf.fill_synthetic(cap - 50, seed=2)
+    g = np.random.default_rng(4)
+    for rnd in range(12):
+        agent.train_ops_n(50, buf)
+        buf.append_rows(g.standard_normal((int(g.integers(1, 40)), buf.row_stride)).astype(np.float32))
+    assert agent.n_runs == 600 and buf.size == cap
+    u = torch.rand(256, generator=torch.Generator().manual_seed(1))
+    buf.zero_copy = False
+    buf._sink = None
+    a = buf.sample(256, u=u)
+    ind_incremental = buf.ind.copy()
+    pri = buf.priority
+    prefix = torch.cumsum(pri[: buf.size], 0)
+    ref_ind = torch.searchsorted(prefix, u * prefix[-1]).numpy()
+    assert np.array_equal(ind_incremental, ref_ind)
+    _lib.check(buf._lib.b200rl_replay_set_cursor(buf._h, 0, buf.ptr, buf.size))  # invalidates the tree: next sample rebuilds it
+    b = buf.sample(256, u=u)
+    assert np.array_equal(buf.ind, ind_incremental)
+    for k in a:
+        assert torch.equal(a[k], b[k])
+    assert float(pri.max()) == pytest.approx(buf.max_priority) or buf.max_priority >= float(pri.max())
+
+
 def test_no_cpu_fallback_paths():
     from sac_td3_td7_b200 import _lib
     from sac_td3_td7_b200.rl import nn as bnn
