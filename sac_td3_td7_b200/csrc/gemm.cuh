@@ -736,11 +736,53 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_cons
   B200_PROBE_END
 }
 
+// ---- bias gradients of stacked seeds --------------------------------------------------------------
+// db[i] = sum_r dZ[r][i] (+ Adam).  As a "B := ones column" problem of the tile kernel a bias gradient costs eight full
+// 32x32 tiles of FFMA for one useful column; for one agent that rides along in a launch that exists anyway, but with
+// hundreds of stacked seeds it is most of the narrow-problem launch.  There (the tensor-core path) bias gradients are
+// column sums: one CTA per (problem, seed), thread i sums column i over the batch with coalesced row reads.
+struct BiasProblem {
+  const float* dZ; long long dz_gs; int dz_ld; int rows, out;
+  float* C; float* P; float* M; float* V; long long p_gs;
+  const AdamScalars* adam;
+};
+struct BiasLaunch {
+  BiasProblem p[kMaxProblems];
+  int nprob;
+  int pad;
+};
+__global__ void __launch_bounds__(256) bias_grad_kernel(const __grid_constant__ BiasLaunch L) {
+  B200_PDL_PROLOGUE();
+  const BiasProblem& bp = L.p[blockIdx.x];
+  const int g = blockIdx.y;
+  const float* dz = bp.dZ + (long long)g * bp.dz_gs;
+  for (int i = threadIdx.x; i < bp.out; i += blockDim.x) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // four independent chains over r mod 4, combined in a fixed order
+    int r = 0;
+    for (; r + 3 < bp.rows; r += 4) {
+      s0 += dz[(long long)(r + 0) * bp.dz_ld + i];
+      s1 += dz[(long long)(r + 1) * bp.dz_ld + i];
+      s2 += dz[(long long)(r + 2) * bp.dz_ld + i];
+      s3 += dz[(long long)(r + 3) * bp.dz_ld + i];
+    }
+    for (; r < bp.rows; ++r) s0 += dz[(long long)r * bp.dz_ld + i];
+    const float gsum = (s0 + s1) + (s2 + s3);
+    const long long o = (long long)g * bp.p_gs + i;
+    if (bp.P) {
+      float p = bp.P[o], m = bp.M[o], v = bp.V[o];
+      adam_update(gsum, p, m, v, *bp.adam);
+      bp.P[o] = p; bp.M[o] = m; bp.V[o] = v;
+    }
+    if (bp.C) bp.C[o] = gsum;
+  }
+}
+
 // ----------------------------------------------------------------------------- host side
 // A launch table: problems are appended on the host once, then replayed (the struct is passed by value
 // as the kernel parameter; scratch / tickets for split-K live in device memory owned by the table).
 struct GemmTable {
   FfmaLaunch launch;      // problems run by the FFMA kernel
+  BiasLaunch launch_bias; // bias gradients of stacked seeds (tensor-core path only)
   GemmLaunch launch_tc;   // problems run by the tcgen05 kernel (stacked seeds; gemm_tc.cuh)
   int nprob = 0;
   int total_tiles = 0;    // FFMA tiles (32 x 32)

@@ -123,13 +123,14 @@ inline bool use_tensor_cores(int groups) {
 
 inline int gemm_table_upload(GemmTable* t, int mode, std::vector<GemmProblem>& probs, DeviceArena* arena, int groups = 1, int force_splitk = 0) {
   B200_REQUIRE((int)probs.size() <= kMaxProblems, "too many problems in one gemm launch");
-  std::vector<GemmProblem> ff, tc;
+  std::vector<GemmProblem> ff, tc, bias;
   const bool want_tc = use_tensor_cores(groups);
   for (auto& p : probs) {
     B200_REQUIRE(p.nseg >= 1 && p.nseg <= 3, "gemm problem needs 1..3 segments");
     B200_REQUIRE(p.I > 0 && p.J > 0, "gemm problem with empty output");
 #ifndef B200_EMU
     if (want_tc && tc_eligible(p)) { tc.push_back(p); continue; }
+    if (want_tc && mode == kWgrad && p.nseg == 1 && p.seg[0].b_ones && p.J == 1) { bias.push_back(p); continue; }
 #endif
     ff.push_back(p);
   }
@@ -167,6 +168,14 @@ inline int gemm_table_upload(GemmTable* t, int mode, std::vector<GemmProblem>& p
   for (size_t i = 0; i < tc.size(); ++i) t->launch_tc.p[i] = tc[i];
   t->launch.nprob = (int)ff.size();
   t->launch.splitk = splitk;
+  memset(&t->launch_bias, 0, sizeof(t->launch_bias));
+  for (size_t i = 0; i < bias.size(); ++i) {  // wgrad_problems(): A = dZ [rows][out], C/P/M/V = the bias vector
+    const GemmProblem& p = bias[i];
+    BiasProblem& b = t->launch_bias.p[i];
+    b.dZ = p.seg[0].A; b.dz_gs = p.seg[0].a_gs; b.dz_ld = p.seg[0].a_ld; b.rows = p.seg[0].len; b.out = p.I;
+    b.C = p.C; b.P = p.P; b.M = p.M; b.V = p.V; b.p_gs = p.P ? p.p_gs : p.c_gs; b.adam = p.adam;
+  }
+  t->launch_bias.nprob = (int)bias.size();
   static int table_counter = 0;
   t->launch.tag = ++table_counter;
   if (getenv("B200RL_DEBUG_TABLES")) {
@@ -203,6 +212,12 @@ inline int gemm_table_launch(const GemmTable& t, int groups, cudaStream_t stream
       case kDgrad: { auto k = gemm_tc_kernel<kDgrad>; B200_LAUNCH(k, grid, block, kTcSmemBytes, stream, t.launch_tc); break; }
       default: { auto k = gemm_tc_kernel<kWgrad>; B200_LAUNCH(k, grid, block, kTcSmemBytes, stream, t.launch_tc); break; }
     }
+    B200_CHECK_LAUNCH();
+  }
+#endif
+#ifndef B200_EMU
+  if (t.launch_bias.nprob > 0) {
+    B200_LAUNCH(bias_grad_kernel, dim3((unsigned)t.launch_bias.nprob, (unsigned)groups), dim3(256), 0, stream, t.launch_bias);
     B200_CHECK_LAUNCH();
   }
 #endif
