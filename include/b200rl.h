@@ -154,6 +154,10 @@ int b200rl_agent_read_info(b200rl_agent* h, int64_t first_step, int count, int g
 int b200rl_agent_act(b200rl_agent* h, const float* obs_dev, float* out_dev, void* stream);
 /* parity probes of the last update: which = 0 q_target[B], 1 priority[B], 2 q1[B], 3 q2[B], 4 pi_action[B][A] */
 int b200rl_agent_debug_read(b200rl_agent* h, int which, int group, float* out_host, void* stream);
+/* the info value `col` of seed 0 for update `step` as soon as the kernel that computes it has run (it is posted to a
+ * pinned host mailbox), without waiting for the rest of the update -- what `float(loss)` (td7.py:303,315,324) needs.
+ * Returns 0 and the value, or 1 when `step` is not the newest update / the value was not posted: read the ring then. */
+int b200rl_agent_wait_info(b200rl_agent* h, int64_t step, int col, float* out);
 /* number of kernel launches issued by the last update (bench: gpu_launches) */
 int b200rl_agent_launches_per_update(b200rl_agent* h, int actor_step);
 

@@ -109,6 +109,7 @@ SIGNATURES = {
     "b200rl_agent_update": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "b200rl_agent_update_n": (C.c_int, [c_vp, c_vp, C.c_int, c_vp]),
     "b200rl_agent_info_cols": (C.c_int, [c_vp]),
+    "b200rl_agent_wait_info": (C.c_int, [c_vp, C.c_int64, C.c_int, C.POINTER(C.c_float)]),
     "b200rl_agent_read_info": (C.c_int, [c_vp, C.c_int64, C.c_int, C.c_int, c_vp, c_vp]),
     "b200rl_agent_act": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "b200rl_agent_debug_read": (C.c_int, [c_vp, C.c_int, C.c_int, c_vp, c_vp]),

@@ -62,6 +62,8 @@ struct AgentBase {
   int nopt = 0;
   float* d_info = nullptr;
   int info_cols = 0;
+  InfoMail* h_mail = nullptr;  // pinned, mapped: losses of seed 0 as soon as their kernel has run (ops.cuh: publish_info)
+  InfoMail* d_mail = nullptr;
   long long n_calls = 0;  // host mirror of StepState.n_runs
   unsigned long long rng_seed = 0xB200B200ULL;
   unsigned low_priority_streams = 0;  // bit i: fork.side[i] carries slack work (set by the subclass before init_common)
@@ -86,6 +88,7 @@ struct AgentBase {
 #endif
     fork.destroy();
     if (stream) cudaStreamDestroy(stream);
+    if (h_mail) cudaFreeHost(h_mail);
   }
 
   Mat alloc_act(int rows, int cols) {
@@ -112,8 +115,17 @@ struct AgentBase {
     B200_TRY(arena.alloc(&d_flags, 4));
     B200_TRY(arena.alloc(&d_info, (size_t)G * kInfoRing * info_cols));
     B200_CHECK_CUDA(cudaMemcpy(d_hyper, hyper, nopt * sizeof(OptimHyper), cudaMemcpyHostToDevice));
+#ifdef B200_EMU
+    B200_CHECK_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_mail), kMailCols * sizeof(InfoMail)));
+    d_mail = h_mail;
+#else
+    B200_CHECK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_mail), kMailCols * sizeof(InfoMail), cudaHostAllocMapped));
+    B200_CHECK_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_mail), h_mail, 0));
+#endif
+    memset(h_mail, 0, kMailCols * sizeof(InfoMail));
     StepState st0;
     memset(&st0, 0, sizeof(st0));
+    st0.mail = d_mail;
     for (int k = 0; k < 4; ++k) st0.b1pow[k] = st0.b2pow[k] = 1.0;
     B200_CHECK_CUDA(cudaMemcpy(d_step, &st0, sizeof(st0), cudaMemcpyHostToDevice));
     return kOk;

@@ -1,5 +1,7 @@
 // api.cuh -- extern "C" entry points declared in include/b200rl.h.
 #pragma once
+#include <atomic>
+#include <chrono>
 #include <cstddef>
 #include <memory>
 
@@ -357,6 +359,7 @@ int b200rl_agent_copy_from(b200rl_agent* dst, const b200rl_agent* src, int full,
     AgentBase& D = *dst->base;
     const AgentBase& C = *src->base;
     B200_CHECK_CUDA(cudaMemcpyAsync(D.d_step, C.d_step, sizeof(StepState), cudaMemcpyDeviceToDevice, s));
+    B200_CHECK_CUDA(cudaMemcpyAsync(&D.d_step->mail, &D.d_mail, sizeof(InfoMail*), cudaMemcpyHostToDevice, s));  // keep its own mailbox
     B200_CHECK_CUDA(cudaMemcpyAsync(D.d_adam, C.d_adam, (size_t)C.nopt * sizeof(AdamScalars), cudaMemcpyDeviceToDevice, s));
     D.n_calls = C.n_calls;
     if (dst->td7) B200_CHECK_CUDA(cudaMemcpyAsync(dst->td7->d_range, src->td7->d_range, (size_t)D.G * sizeof(TD7Range), cudaMemcpyDeviceToDevice, s));
@@ -484,6 +487,27 @@ int b200rl_agent_read_info(b200rl_agent* h, int64_t first_step, int count, int g
   return kOk;
 }
 
+int b200rl_agent_wait_info(b200rl_agent* h, int64_t step, int col, float* out) {
+  B200_REQUIRE(h && out, "null argument");
+  AgentBase& a = *h->base;
+  if (!a.h_mail || col < 0 || col >= kMailCols || step != a.n_calls) return 1;  // not the newest update: read the ring
+  const volatile unsigned long long* m = &a.h_mail[col].bits;
+  const auto t0 = std::chrono::steady_clock::now();
+  long spins = 0;
+  unsigned long long x;
+  while ((int)((x = *m) >> 32) < (int)step) {
+    if ((++spins & 0xfff) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(2)) return 1;  // never posted: read the ring
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+  if ((int)(x >> 32) != (int)step) return 1;  // a later update already posted over it
+  const unsigned lo = (unsigned)(x & 0xffffffffull);
+  float v;
+  memcpy(&v, &lo, sizeof(v));
+  *out = v;
+  return kOk;
+}
 int b200rl_agent_act(b200rl_agent* h, const float* obs_dev, float* out_dev, void* stream) {
   B200_REQUIRE(h && obs_dev && out_dev, "null argument");
   AgentBase& a = *h->base;

@@ -74,6 +74,12 @@ __global__ void __launch_bounds__(256) avgl1norm_kernel(const RowOp* __restrict_
 struct OptimHyper {
   double lr, beta1, beta2, eps;
 };
+// Host-visible mailbox (pinned, mapped memory): the kernel that produces an info value of seed 0 also posts it here as
+// ONE 8-byte store {value bits, update number} -- a single posted write, so no system-scope fence is needed to order
+// value and tag (a fence.sys costs ~1.5 us on the chain) -- and the host can read a loss the moment it exists, without
+// waiting for the rest of the update graph, by polling the tag (b200rl_agent_wait_info).
+struct InfoMail { unsigned long long bits; };  // low 32: float bits, high 32: update number
+constexpr int kMailCols = 8;
 // device-resident counters shared by the update graphs
 struct StepState {
   int n_runs;         // number of completed train_ops calls (TD7 semantics: incremented first)
@@ -82,7 +88,13 @@ struct StepState {
   int pad[2];
   double b1pow[4];    // beta1^t, beta2^t per optimizer, carried as running products (1.0 at t = 0)
   double b2pow[4];
+  InfoMail* mail;     // device address of the host mailbox (null: none)
 };
+__device__ __forceinline__ void publish_info(const StepState* st, long long g, int col, float v) {
+  if (g != 0 || st->mail == nullptr || col < 0 || col >= kMailCols) return;
+  const unsigned long long packed = ((unsigned long long)(unsigned)st->n_runs << 32) | (unsigned long long)__float_as_uint(v);
+  *reinterpret_cast<volatile unsigned long long*>(&st->mail[col].bits) = packed;
+}
 
 // one thread: advance counters and refresh the Adam scalars of the optimizers that step now
 __global__ void prep_step_kernel(StepState* st, AdamScalars* adam, const OptimHyper* hyper, int nopt, unsigned step_mask, int ring) {
@@ -180,6 +192,7 @@ __global__ void __launch_bounds__(256) grad_norm_sum_kernel(const float* __restr
   total += (double)sqrtf((float)acc);
   (void)nslices;
   info[g * info_gs + (long long)st->info_slot * info_stride + info_col] = (float)total;
+  publish_info(st, g, info_col, (float)total);
   counter[g] = 0u;  // ready for the next replay of the graph
 }
 
@@ -285,6 +298,7 @@ __global__ void __launch_bounds__(256) td7_encoder_loss_kernel(const float* __re
     double tot = 0.0;
     for (unsigned k = 0; k < gridDim.x; ++k) tot += (double)partial[g * gridDim.x + k];
     info[g * info_gs + (long long)st->info_slot * info_stride + info_col] = (float)(tot / ((double)B * (double)Z));
+    publish_info(st, g, info_col, (float)(tot / ((double)B * (double)Z)));
     counter[g] = 0;
   }
 }
@@ -365,7 +379,10 @@ __global__ void __launch_bounds__(1024) critic_loss_kernel(CriticLossArgs a) {
     a.dq2[o + b] = g2;
   }
   const float tot = block_sum_256(l, red);
-  if (b == 0) a.info[g * a.info_gs + (long long)a.st->info_slot * a.info_stride + a.info_col] = tot * invB;
+  if (b == 0) {
+    a.info[g * a.info_gs + (long long)a.st->info_slot * a.info_stride + a.info_col] = tot * invB;
+    publish_info(a.st, g, a.info_col, tot * invB);
+  }
   if (a.use_lap) {
     const float p = (b < B) ? powf(fmaxf(fmaxf(td1, td2), 1.0f), 0.4f) : 0.f;
     if (a.prio_out && b < B) a.prio_out[o + b] = p;
@@ -383,7 +400,10 @@ __global__ void __launch_bounds__(1024) td7_actor_loss_kernel(const float* __res
   const int g = blockIdx.x, b = threadIdx.x;
   float v = (b < B) ? (q1[g * gs + b] + q2[g * gs + b]) : 0.f;
   const float tot = block_sum_256(v, red);
-  if (b == 0) info[g * info_gs + (long long)st->info_slot * info_stride + info_col] = -tot / (2.0f * (float)B);
+  if (b == 0) {
+    info[g * info_gs + (long long)st->info_slot * info_stride + info_col] = -tot / (2.0f * (float)B);
+    publish_info(st, g, info_col, -tot / (2.0f * (float)B));
+  }
 }
 
 // actor loss TD3 / SAC: L = mean(-min(q1,q2) [+ alpha*logp]); gradient of min splits evenly on ties.
@@ -423,7 +443,10 @@ __global__ void __launch_bounds__(1024) minq_actor_loss_kernel(ActorLossArgs a) 
   const float pol = block_sum_256(term, red) * invB;
   float* info = a.info + g * a.info_gs + (long long)a.st->info_slot * a.info_stride;
   if (!sac) {
-    if (b == 0 && a.col_policy >= 0) info[a.col_policy] = pol;
+    if (b == 0 && a.col_policy >= 0) {
+      info[a.col_policy] = pol;
+      publish_info(a.st, g, a.col_policy, pol);
+    }
     return;
   }
   const float slp = block_sum_256(b < B ? lp : 0.f, red);
@@ -434,12 +457,12 @@ __global__ void __launch_bounds__(1024) minq_actor_loss_kernel(ActorLossArgs a) 
   }
   if (b == 0) {
     // the reference logs policy_obj AFTER `obj += tmp_loss` mutated it in place
-    if (a.col_policy >= 0) info[a.col_policy] = a.log_alpha ? pol + tl : pol;
-    if (a.col_entropy >= 0) info[a.col_entropy] = -slp * invB;
+    if (a.col_policy >= 0) { info[a.col_policy] = a.log_alpha ? pol + tl : pol; publish_info(a.st, g, a.col_policy, a.log_alpha ? pol + tl : pol); }
+    if (a.col_entropy >= 0) { info[a.col_entropy] = -slp * invB; publish_info(a.st, g, a.col_entropy, -slp * invB); }
     if (a.log_alpha) {
-      if (a.col_tmp_loss >= 0) info[a.col_tmp_loss] = tl;
-      if (a.col_alpha >= 0) info[a.col_alpha] = alpha;
-      if (a.col_tmp_grad >= 0) info[a.col_tmp_grad] = tl;
+      if (a.col_tmp_loss >= 0) { info[a.col_tmp_loss] = tl; publish_info(a.st, g, a.col_tmp_loss, tl); }
+      if (a.col_alpha >= 0) { info[a.col_alpha] = alpha; publish_info(a.st, g, a.col_alpha, alpha); }
+      if (a.col_tmp_grad >= 0) { info[a.col_tmp_grad] = tl; publish_info(a.st, g, a.col_tmp_grad, tl); }
       a.grad_log_alpha[g] = tl;
     }
   }

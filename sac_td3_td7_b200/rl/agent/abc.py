@@ -38,7 +38,7 @@ class LazyScalar:
 
     def __float__(self):
         if self._val is None:
-            self._val = float(self._agent._info_row(self._step)[self._col])
+            self._val = self._agent._info_value(self._step, self._col)
             self._agent = None
         return self._val
 
@@ -204,6 +204,17 @@ class Agent(ABC):
             self._write_net(nid, modules[attr], names, group=seed)
 
     # ------------------------------------------------------------------ info ring
+    def _info_value(self, step: int, col: int) -> float:
+        """One info value.  For the newest update of a single agent the engine posts every loss to a pinned host mailbox
+        the moment its kernel has run (b200rl_agent_wait_info), so ``float(info["train/q_fn"])`` returns while the
+        backward pass of that update is still executing; anything else comes from the device ring."""
+        row = self._info_cache.get(step)
+        if row is None and step == self._n_calls and self.n_seeds == 1 and col < 8:
+            v = C.c_float()
+            if self._lib.b200rl_agent_wait_info(self._h, step, col, C.byref(v)) == 0:
+                return float(v.value)
+        return float(self._info_row(step)[col])
+
     def _info_row(self, step):
         """Row `step` (1-based train_ops count) of the device info ring; one D2H fetches every row
         from `step` to the newest, so reading a burst of infos costs a single sync."""

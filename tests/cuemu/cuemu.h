@@ -306,6 +306,7 @@ static inline void __syncthreads() { cuemu::block_barrier(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { cuemu::warp_barrier(); }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
 template <class T> static inline T __shfl_sync(unsigned, T v, int src, int = 32) { return cuemu::shfl_from(v, src); }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m, int = 32) { return cuemu::shfl_from(v, cuemu::cur_lane() ^ m); }

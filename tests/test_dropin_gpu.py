@@ -279,6 +279,23 @@ def test_sum_tree_stays_exact_over_a_long_run():
     assert float(pri.max()) == pytest.approx(buf.max_priority) or buf.max_priority >= float(pri.max())
 
 
+@pytest.mark.parametrize("name", ["td7_halfcheetah_lap", "td3_hopper_uniform", "sac_walker2d"])
+def test_losses_posted_to_the_host_mailbox_equal_the_ring(name):
+    """float(info[k]) of the newest update is served from the pinned host mailbox (posted by the kernel that computes
+    the value, before the rest of the update has run); it must be bit-identical to the device info ring, for every
+    key of every step, and older updates must still be readable from the ring."""
+    agent, buf, algo, _ = _mk(name)
+    kept = []
+    for t in range(6):
+        info = agent.train_ops(buf.sample(gu.BATCH), replay_buffer=buf)
+        step = agent._n_calls
+        got = {k: (None if v is None else float(v)) for k, v in info.items()}
+        assert got == agent.info_dicts(step, 1)[0], (t, got)
+        kept.append((step, agent._info_dict(step, agent._actor_step(step))))
+    for step, lazy in kept[:-1]:  # not the newest any more: ring path
+        assert {k: (None if v is None else float(v)) for k, v in lazy.items()} == agent.info_dicts(step, 1)[0]
+
+
 def test_no_cpu_fallback_paths():
     from sac_td3_td7_b200 import _lib
     from sac_td3_td7_b200.rl import nn as bnn
