@@ -779,7 +779,7 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const __grid_constant__ 
 
 // ----------------------------------------------------------------------------- host side
 // A launch table: problems are appended on the host once, then replayed (the struct is passed by value
-// as the kernel parameter; scratch / tickets for split-K live in device memory owned by the table).
+// as the kernel parameter; nothing lives in device memory).
 struct GemmTable {
   FfmaLaunch launch;      // problems run by the FFMA kernel
   BiasLaunch launch_bias; // bias gradients of stacked seeds (tensor-core path only)
