@@ -100,6 +100,7 @@ struct MlpAgent : AgentBase {
     layout_acts();
     B200_TRY(build_tables());
     B200_TRY(sync());
+    B200_CHECK_CUDA(cudaDeviceSynchronize());  // (uploads above went through the legacy default stream; the engine runs on non-blocking ones)
     return kOk;
   }
 

@@ -112,6 +112,7 @@ struct TD7Agent : AgentBase {
     B200_CHECK_LAUNCH();
     B200_TRY(build_tables());
     B200_TRY(sync());
+    B200_CHECK_CUDA(cudaDeviceSynchronize());  // (uploads above went through the legacy default stream; the engine runs on non-blocking ones)
     return kOk;
   }
 

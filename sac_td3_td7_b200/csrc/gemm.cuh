@@ -116,6 +116,11 @@ struct GemmLaunch {
   GemmProblem p[kMaxProblems];
   int nprob;
   int total_tiles;
+  // forward problems whose operands TMA can address (16-byte aligned bases and row strides): bit pi of tma_mask, and
+  // tmaps = device array of CUtensorMap [problem][segment][A, B] (gemm_tc.cuh)
+  unsigned tma_mask;
+  int pad;
+  const void* tmaps;
 };
 
 // Device-side form of a problem for the FFMA kernel: GemmProblem plus everything the host can work out
@@ -789,6 +794,7 @@ struct GemmTable {
   int tc_tiles = 0;       // tcgen05 tiles (128 rows x N)
   int mode = kFwd;
   int groups = 1;
+  bool debug_print = false;
 };
 
 }  // namespace b200rl

@@ -33,7 +33,7 @@ constexpr int kTcThreads = 256;
 constexpr int kTcATileBytes = kTcM * 128;                       // 16 KB
 constexpr int kTcBTileBytes = kTcNMax * 128;                    // 32 KB
 constexpr int kTcStageBytes = kTcATileBytes + kTcBTileBytes;    // 48 KB
-constexpr int kTcSmemBytes = 1024 + kTcStages * kTcStageBytes + 64;
+constexpr int kTcSmemBytes = 1024 + kTcStages * kTcStageBytes + 64;  // + alignment slack + 2 x kTcStages mbarriers
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -57,6 +57,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (ok) return;
     if (spin > (1u << 22)) __trap();
   }
+}
+// ---- TMA (cp.async.bulk.tensor): one thread moves a whole operand tile into the UMMA SWIZZLE_128B layout ----
+constexpr int kTmapBytes = 128;  // sizeof(CUtensorMap)
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(smem_u32(smem_dst)),
+               "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(smem_u32(smem_dst)),
+               "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
@@ -200,6 +215,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) gemm_tc_kernel(const __grid_con
   // SWIZZLE_128B tiles need 1024-byte alignment
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcStages * kTcStageBytes);  // [kTcStages] "stage free"
+  uint64_t* full = bars + kTcStages;                                                // [kTcStages] "stage filled" (TMA path)
   __shared__ uint32_t s_tmem_base;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -217,7 +233,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) gemm_tc_kernel(const __grid_con
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
   if (tid == 32) {
-    for (int s = 0; s < kTcStages; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(&bars[s], 1); mbar_init(&full[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   tc_fence_before();
@@ -228,6 +244,53 @@ __global__ void __launch_bounds__(kTcThreads, 2) gemm_tc_kernel(const __grid_con
   int total_chunks = 0;
   for (int s = 0; s < sp.nseg; ++s) total_chunks += (sp.seg[s].len + kTcBK - 1) / kTcBK;
 
+  const uint32_t idesc = tc_instr_desc(n_pad, !A_KM, !B_KM);
+  const uint32_t smem_base_u32 = smem_u32(smem);
+  if ((L.tma_mask >> pi) & 1u) {
+    // ---- TMA main loop: thread 0 is producer and MMA issuer; nobody stages anything, nobody synchronises per chunk.
+    // For chunk c it first refills the stage freed by the MMAs of chunk c-1 (tile of chunk c+S-1: one bulk tensor copy
+    // per operand, completing on full[stage] with the box byte count), then waits for chunk c's tile and issues its MMAs.
+    if (tid == 0) {
+      const unsigned char* maps = reinterpret_cast<const unsigned char*>(L.tmaps) + (size_t)pi * 6 * kTmapBytes;
+      const uint32_t tx_bytes = (uint32_t)(kTcM * 128 + J * 128);
+      int lseg = 0, lr0 = 0;  // (segment, reduction offset) of the next chunk to load
+      auto load_chunk = [&](int stage) {
+        unsigned char* At = smem + stage * kTcStageBytes;
+        mbar_expect_tx(&full[stage], tx_bytes);
+        // K-major operand: 3-D tensor {r, output index, seed}; MN-major: 4-D {32 output indices, r, 32-index block, seed}
+        if (A_KM) tma_load_3d(At, maps + (lseg * 2 + 0) * kTmapBytes, lr0, i0, g, &full[stage]);
+        else tma_load_4d(At, maps + (lseg * 2 + 0) * kTmapBytes, 0, lr0, i0 / 32, g, &full[stage]);
+        if (B_KM) tma_load_3d(At + kTcATileBytes, maps + (lseg * 2 + 1) * kTmapBytes, lr0, 0, g, &full[stage]);
+        else tma_load_4d(At + kTcATileBytes, maps + (lseg * 2 + 1) * kTmapBytes, 0, lr0, 0, g, &full[stage]);
+        lr0 += kTcBK;
+        if (lr0 >= sp.seg[lseg].len) { ++lseg; lr0 = 0; }
+      };
+      for (int s = 0; s < kTcStages - 1 && s < total_chunks; ++s) load_chunk(s);
+      for (int c = 0; c < total_chunks; ++c) {
+        const int s = c % kTcStages;
+        const int cn = c + kTcStages - 1;
+        if (cn < total_chunks) {
+          if (c >= 1) mbar_wait(&bars[cn % kTcStages], (uint32_t)(((c - 1) / kTcStages) & 1));
+          load_chunk(cn % kTcStages);
+        }
+        mbar_wait(&full[s], (uint32_t)((c / kTcStages) & 1));
+        tc_fence_after();
+        const uint32_t a_addr = smem_base_u32 + s * kTcStageBytes;
+        const uint32_t b_addr = a_addr + kTcATileBytes;
+#pragma unroll
+        for (int kk = 0; kk < kTcBK / 8; ++kk) {
+          const uint64_t da = A_KM ? tc_smem_desc(a_addr + kk * 32, 16, 1024, 2) : tc_smem_desc(a_addr + kk * 1024, 4096, 512, 1);
+          const uint64_t db = B_KM ? tc_smem_desc(b_addr + kk * 32, 16, 1024, 2) : tc_smem_desc(b_addr + kk * 1024, 4096, 512, 1);
+          tc_mma_tf32(tmem_base, da, db, idesc, (c > 0 || kk > 0) ? 1u : 0u);
+        }
+        tc_commit(&bars[s]);
+      }
+      if (total_chunks > 0) {
+        const int last = total_chunks - 1;
+        mbar_wait(&bars[last % kTcStages], (uint32_t)((last / kTcStages) & 1));
+      }
+    }
+  } else {
   TcOperand<kTcM, A_KM> ca;
   TcOperand<kTcNMax, B_KM> cb;
   int pseg = 0, pr0 = 0, plen = 0;
@@ -248,8 +311,6 @@ __global__ void __launch_bounds__(kTcThreads, 2) gemm_tc_kernel(const __grid_con
   };
   open_segment();
 
-  const uint32_t idesc = tc_instr_desc(n_pad, !A_KM, !B_KM);
-  const uint32_t smem_base_u32 = smem_u32(smem);
 
   // prologue
 #pragma unroll
@@ -292,6 +353,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) gemm_tc_kernel(const __grid_con
   if (total_chunks > 0 && tid == 0) {
     const int last = total_chunks - 1;
     mbar_wait(&bars[last % kTcStages], (uint32_t)((last / kTcStages) & 1));
+  }
   }
   tc_fence_before();
   __syncthreads();

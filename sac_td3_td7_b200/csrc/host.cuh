@@ -5,6 +5,10 @@
 #include <mutex>
 #include <vector>
 
+#ifndef B200_EMU
+#include <cuda.h>  // CUtensorMap + the cuTensorMapEncodeTiled prototype (header only: the symbol is fetched at run time)
+#endif
+
 #include "common.cuh"
 #include "gemm.cuh"
 #include "gemm_tc.cuh"
@@ -37,6 +41,9 @@ struct DeviceArena {
     if (bytes == 0) bytes = sizeof(T);
     B200_CHECK_CUDA(cudaMalloc(&p, bytes));
     B200_CHECK_CUDA(cudaMemset(p, 0, bytes));
+    // cudaMemset on device memory is ordered on the legacy default stream only and may return before it has run; the
+    // engines work on non-blocking streams, so without this a later fill / upload could be overwritten by the zeroing
+    B200_CHECK_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
     blocks.push_back(p);
     total_bytes += bytes;
     *out = reinterpret_cast<T*>(p);
@@ -121,6 +128,55 @@ inline bool use_tensor_cores(int groups) {
 #endif
 }
 
+#ifndef B200_EMU
+// ---- TMA descriptors for the tcgen05 forward problems --------------------------------------------------------------
+// Operand of one reduction segment as a 3-D fp32 tensor {reduction index, output index, stacked seed}; box = one
+// pipeline stage tile {32, rows, 1}, SWIZZLE_128B -- which is byte for byte the UMMA K-major canonical layout the
+// kernel's shared-memory descriptors expect.  Out-of-range reduction indices (segment tails such as the 8 action
+// columns) are zero-filled by the TMA unit.
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn tma_encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    (void)cudaGetLastError();
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+inline bool tma_operand_ok(const float* base, int ld, long long gs, int groups) {
+  return base && (reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld & 3) == 0 && ld > 0 && (groups == 1 || ((gs & 3) == 0 && gs > 0));
+}
+inline bool tma_make_map(CUtensorMap* m, const float* base, int ld, long long gs, int len, int rows, int box_rows, int groups) {
+  EncodeTiledFn fn = tma_encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)len, (cuuint64_t)rows, (cuuint64_t)groups};
+  const cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(groups > 1 ? gs : (long long)rows * ld) * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// MN-major operand (contiguous along the output index c in global memory): 4-D tensor {32 c, r, c / 32, seed}, box
+// {32, 32, blocks, 1}, SWIZZLE_128B_ATOM_32B = the UMMA SWIZZLE_128B_BASE32B MN-major layout (4 KB per 32-index block)
+inline bool tma_make_map_mn(CUtensorMap* m, const float* base, int ld, long long gs, int len, int cols, int box_blocks, int groups) {
+  EncodeTiledFn fn = tma_encode_fn();
+  if (!fn || (cols & 31) != 0) return false;
+  const cuuint64_t dims[4] = {32u, (cuuint64_t)len, (cuuint64_t)(cols / 32), (cuuint64_t)groups};
+  const cuuint64_t strides[3] = {(cuuint64_t)ld * 4, 128u, (cuuint64_t)(groups > 1 ? gs : (long long)len * ld) * 4};
+  const cuuint32_t box[4] = {32u, (cuuint32_t)kTcBK, (cuuint32_t)box_blocks, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+inline bool use_tma() {
+  static const bool on = [] { const char* e = getenv("B200RL_TC_TMA"); return e ? atoi(e) != 0 : true; }();  // B200RL_TC_TMA=0: cp.async staging
+  return on;
+}
+#endif
+
 inline int gemm_table_upload(GemmTable* t, int mode, std::vector<GemmProblem>& probs, DeviceArena* arena, int groups = 1, int force_splitk = 0) {
   B200_REQUIRE((int)probs.size() <= kMaxProblems, "too many problems in one gemm launch");
   std::vector<GemmProblem> ff, tc, bias;
@@ -163,7 +219,6 @@ inline int gemm_table_upload(GemmTable* t, int mode, std::vector<GemmProblem>& p
   splitk = 1;
 #endif
   B200_REQUIRE(splitk >= 1 && splitk <= kMaxSplitK, "split-K factor out of range");
-  (void)arena;
   for (size_t i = 0; i < ff.size(); ++i) t->launch.p[i] = make_ffma_problem(ff[i], splitk);
   for (size_t i = 0; i < tc.size(); ++i) t->launch_tc.p[i] = tc[i];
   t->launch.nprob = (int)ff.size();
@@ -183,8 +238,37 @@ inline int gemm_table_upload(GemmTable* t, int mode, std::vector<GemmProblem>& p
     for (auto& p : ff) mc = std::max(mc, chunks_of(p));
     fprintf(stderr, "[b200rl] gemm table %d mode=%d problems=%zu (+%zu tc) tiles=%d groups=%d max_chunks=%d splitk=%d\n", t->launch.tag, mode, ff.size(),
             tc.size(), tiles, groups, mc, splitk);
+    t->debug_print = true;
   }
   t->launch_tc.nprob = (int)tc.size();
+#ifndef B200_EMU
+  if (!tc.empty() && use_tma()) {
+    const bool a_km = (mode != kWgrad), b_km = (mode == kFwd);
+    std::vector<CUtensorMap> maps(tc.size() * 6);
+    unsigned mask = 0;
+    for (size_t i = 0; i < tc.size(); ++i) {
+      const GemmProblem& p = tc[i];
+      bool ok = (p.J % 8) == 0 && p.J <= 256 && (b_km || (p.J % 32) == 0);
+      for (int sgi = 0; sgi < p.nseg && ok; ++sgi) {
+        const GemmSeg& sg = p.seg[sgi];
+        ok = tma_operand_ok(sg.A, sg.a_ld, sg.a_gs, groups) && tma_operand_ok(sg.B, sg.b_ld, sg.b_gs, groups);
+        if (ok) ok = a_km ? tma_make_map(&maps[i * 6 + sgi * 2 + 0], sg.A, sg.a_ld, sg.a_gs, sg.len, p.I, kTcM, groups)
+                          : tma_make_map_mn(&maps[i * 6 + sgi * 2 + 0], sg.A, sg.a_ld, sg.a_gs, sg.len, p.I, kTcM / 32, groups);
+        if (ok) ok = b_km ? tma_make_map(&maps[i * 6 + sgi * 2 + 1], sg.B, sg.b_ld, sg.b_gs, sg.len, p.J, p.J, groups)
+                          : tma_make_map_mn(&maps[i * 6 + sgi * 2 + 1], sg.B, sg.b_ld, sg.b_gs, sg.len, p.J, p.J / 32, groups);
+      }
+      if (ok) mask |= 1u << i;
+    }
+    if (mask) {
+      CUtensorMap* d_maps = nullptr;
+      B200_TRY(arena->alloc(&d_maps, maps.size()));
+      B200_CHECK_CUDA(cudaMemcpy(d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+      t->launch_tc.tmaps = d_maps;
+      t->launch_tc.tma_mask = mask;
+    }
+    if (t->debug_print) fprintf(stderr, "[b200rl]   tcgen05 problems fed by TMA: mask 0x%x of %zu\n", mask, tc.size());
+  }
+#endif
   t->launch_tc.total_tiles = tct;
   return kOk;
 }
