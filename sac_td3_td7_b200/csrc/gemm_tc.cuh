@@ -206,6 +206,103 @@ struct TcOperand {
   }
 };
 
+// Epilogue of one warp: its 32 output rows (TMEM lanes [32*rowgrp, +32) of the accumulator at `tmem_acc`) x the 128
+// columns starting at `colhalf`.  tcgen05.ld hands every thread one ROW (32 consecutive columns); going to global memory
+// like that would make each warp instruction touch 32 different rows.  So each 32x32 block is transposed through a padded
+// shared-memory tile `st` (32 x 33 floats, private to the warp) and written row by row with lane = column: every global
+// access of the epilogue -- C, bias, aux, and Adam's p/m/v -- is a coalesced 128-byte line.
+template <int MODE>
+__device__ __forceinline__ void tc_epilogue_warp(const GemmProblem& sp, int g, int I, int J, int n_pad, int i0, int rowgrp, int colhalf, float* st, int lane,
+                                                 uint32_t tmem_acc, int total_chunks, int ncb = 4) {
+  const int row_base = i0 + 32 * rowgrp;
+#pragma unroll 1
+  for (int cc = 0; cc < ncb; ++cc) {
+    const int col0 = colhalf + cc * 32;
+    if (col0 >= n_pad) break;  // uniform across the warp
+    {
+      float v[32];
+      if (total_chunks > 0) {
+        tc_ld32(tmem_acc + ((uint32_t)(32 * rowgrp) << 16) + (uint32_t)col0, v);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 32; ++e) st[lane * 33 + e] = v[e];
+    }
+    __syncwarp();
+    const int col = col0 + lane;
+    const bool col_ok = col < J;
+    const int nrows = min(32, I - row_base);
+    constexpr int U = 8;  // rows in flight: all global loads of a batch are issued before the first use
+    if (MODE == kFwd) {
+      // (the smoothing-noise epilogue never reaches this kernel: its layer has J = action_dim < 64)
+      const float bias = (sp.bias && col_ok) ? sp.bias[(long long)g * sp.bias_gs + col] : 0.f;
+      float* cptr = sp.C + (long long)g * sp.c_gs + (long long)row_base * sp.c_ld + col;
+      if (col_ok) {
+        for (int rr = 0; rr < nrows; ++rr) {
+          *cptr = act_forward(st[rr * 33 + lane] + bias, sp.act);
+          cptr += sp.c_ld;
+        }
+      }
+    } else if (MODE == kDgrad) {
+      float* cbase = sp.C + (long long)g * sp.c_gs + (long long)row_base * sp.c_ld + col;
+      const float* hbase = sp.aux ? sp.aux + (long long)g * sp.aux_gs + (long long)row_base * sp.aux_ld + col : nullptr;
+      const bool acc_in = sp.accumulate != 0;
+      for (int r0 = 0; r0 < nrows; r0 += U) {
+        float hv[U], cv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const bool ok = col_ok && r0 + u < nrows;
+          hv[u] = (hbase && ok) ? hbase[(long long)(r0 + u) * sp.aux_ld] : 0.f;
+          cv[u] = (acc_in && ok) ? cbase[(long long)(r0 + u) * sp.c_ld] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (col_ok && r0 + u < nrows) {
+            float x = st[(r0 + u) * 33 + lane] + cv[u];
+            if (hbase) x *= act_backward(hv[u], sp.act);
+            cbase[(long long)(r0 + u) * sp.c_ld] = x;
+          }
+        }
+      }
+    } else {
+      AdamScalars sc;
+      if (sp.P) sc = *sp.adam;
+      const long long poff = (long long)g * sp.p_gs + (long long)row_base * sp.p_ld + col;
+      float* cbase = sp.C ? sp.C + (long long)g * sp.c_gs + (long long)row_base * sp.c_ld + col : nullptr;
+      for (int r0 = 0; r0 < nrows; r0 += U) {
+        float pv[U], mv[U], vv[U];
+        if (sp.P) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const bool ok = col_ok && r0 + u < nrows;
+            const long long o = poff + (long long)(r0 + u) * sp.p_ld;
+            pv[u] = ok ? sp.P[o] : 0.f;
+            mv[u] = ok ? sp.M[o] : 0.f;
+            vv[u] = ok ? sp.V[o] : 0.f;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (col_ok && r0 + u < nrows) {
+            const float gval = st[(r0 + u) * 33 + lane];
+            if (sp.P) {
+              const long long o = poff + (long long)(r0 + u) * sp.p_ld;
+              adam_update(gval, pv[u], mv[u], vv[u], sc);
+              sp.P[o] = pv[u];
+              sp.M[o] = mv[u];
+              sp.V[o] = vv[u];
+            }
+            if (cbase) cbase[(long long)(r0 + u) * sp.c_ld] = gval;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kTcThreads, 2) gemm_tc_kernel(const __grid_constant__ GemmLaunch L) {
   B200_PDL_PROLOGUE();
@@ -359,105 +456,152 @@ __global__ void __launch_bounds__(kTcThreads, 2) gemm_tc_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
 
-  // ---- epilogue ----
-  // warp w owns TMEM lanes [32*(w&3), +32) (its 32 output rows) and columns [128*(w>>2), +128).  tcgen05.ld
-  // hands every thread one ROW (32 consecutive columns); going to global memory like that would make each
-  // warp instruction touch 32 different rows.  So each 32x32 block is transposed through a padded
-  // shared-memory tile (the pipeline stages are free now) and written row by row with lane = column:
-  // every global access of the epilogue -- C, bias, aux, and Adam's p/m/v -- is a coalesced 128-byte line.
-  float* st = reinterpret_cast<float*>(smem) + warp * (32 * 33);
-  const int row_base = i0 + 32 * (warp & 3);
-  const int colhalf = (warp >> 2) * 128;
-#pragma unroll 1
-  for (int cc = 0; cc < 4; ++cc) {
-    const int col0 = colhalf + cc * 32;
-    if (col0 >= n_pad) break;  // uniform across the warp
-    {
-      float v[32];
-      if (total_chunks > 0) {
-        tc_ld32(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0, v);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] = 0.f;
-      }
-#pragma unroll
-      for (int e = 0; e < 32; ++e) st[lane * 33 + e] = v[e];
-    }
-    __syncwarp();
-    const int col = col0 + lane;
-    const bool col_ok = col < J;
-    const int nrows = min(32, I - row_base);
-    constexpr int U = 8;  // rows in flight: all global loads of a batch are issued before the first use
-    if (MODE == kFwd) {
-      // (the smoothing-noise epilogue never reaches this kernel: its layer has J = action_dim < 64)
-      const float bias = (sp.bias && col_ok) ? sp.bias[(long long)g * sp.bias_gs + col] : 0.f;
-      float* cptr = sp.C + (long long)g * sp.c_gs + (long long)row_base * sp.c_ld + col;
-      if (col_ok) {
-        for (int rr = 0; rr < nrows; ++rr) {
-          *cptr = act_forward(st[rr * 33 + lane] + bias, sp.act);
-          cptr += sp.c_ld;
-        }
-      }
-    } else if (MODE == kDgrad) {
-      float* cbase = sp.C + (long long)g * sp.c_gs + (long long)row_base * sp.c_ld + col;
-      const float* hbase = sp.aux ? sp.aux + (long long)g * sp.aux_gs + (long long)row_base * sp.aux_ld + col : nullptr;
-      const bool acc_in = sp.accumulate != 0;
-      for (int r0 = 0; r0 < nrows; r0 += U) {
-        float hv[U], cv[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const bool ok = col_ok && r0 + u < nrows;
-          hv[u] = (hbase && ok) ? hbase[(long long)(r0 + u) * sp.aux_ld] : 0.f;
-          cv[u] = (acc_in && ok) ? cbase[(long long)(r0 + u) * sp.c_ld] : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (col_ok && r0 + u < nrows) {
-            float x = st[(r0 + u) * 33 + lane] + cv[u];
-            if (hbase) x *= act_backward(hv[u], sp.act);
-            cbase[(long long)(r0 + u) * sp.c_ld] = x;
-          }
-        }
-      }
-    } else {
-      AdamScalars sc;
-      if (sp.P) sc = *sp.adam;
-      const long long poff = (long long)g * sp.p_gs + (long long)row_base * sp.p_ld + col;
-      float* cbase = sp.C ? sp.C + (long long)g * sp.c_gs + (long long)row_base * sp.c_ld + col : nullptr;
-      for (int r0 = 0; r0 < nrows; r0 += U) {
-        float pv[U], mv[U], vv[U];
-        if (sp.P) {
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const bool ok = col_ok && r0 + u < nrows;
-            const long long o = poff + (long long)(r0 + u) * sp.p_ld;
-            pv[u] = ok ? sp.P[o] : 0.f;
-            mv[u] = ok ? sp.M[o] : 0.f;
-            vv[u] = ok ? sp.V[o] : 0.f;
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (col_ok && r0 + u < nrows) {
-            const float gval = st[(r0 + u) * 33 + lane];
-            if (sp.P) {
-              const long long o = poff + (long long)(r0 + u) * sp.p_ld;
-              adam_update(gval, pv[u], mv[u], vv[u], sc);
-              sp.P[o] = pv[u];
-              sp.M[o] = mv[u];
-              sp.V[o] = vv[u];
-            }
-            if (cbase) cbase[(long long)(r0 + u) * sp.c_ld] = gval;
-          }
-        }
-      }
-    }
-    __syncwarp();
-  }
+  // ---- epilogue: warp w owns rows [32*(w&3), +32) and columns [128*(w>>2), +128); the pipeline stages are free now
+  // and serve as the warps' transposition tiles ----
+  tc_epilogue_warp<MODE>(sp, g, I, J, n_pad, i0, warp & 3, (warp >> 2) * 128, reinterpret_cast<float*>(smem) + warp * (32 * 33), lane, tmem_base, total_chunks);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+// ---- persistent, warp-specialised variant (TMA-fed problems only) ----------------------------------------------------
+// One CTA per SM walks the (seed, tile) work list.  Warp 0 (one lane) is the TMA producer and runs ahead through a ring of
+// kWsStages operand stages; warp 1 (one lane) issues the tcgen05 MMAs into one of TWO TMEM accumulators (2 x 256 columns);
+// warps 4..11 are the epilogue: they drain accumulator a while the MMAs of the next tile fill accumulator a^1, so the
+// transposing, HBM-bound epilogue (Adam state!) overlaps the operand stream of the next tile instead of leaving the SM's
+// load pipeline empty.  mbarriers: full[s] (TMA bytes landed) / empty[s] (tcgen05.commit: MMAs done reading the stage),
+// acc_full[a] (tcgen05.commit after the tile's last MMA) / acc_empty[a] (one arrive per epilogue warp).
+constexpr int kWsStages = 3;
+#ifndef B200RL_WS_EPI
+#define B200RL_WS_EPI 16
+#endif
+constexpr int kWsEpiWarps = B200RL_WS_EPI;                 // 8: two column halves; 16: four column quarters
+constexpr int kWsThreads = (4 + kWsEpiWarps) * 32;
+constexpr int kWsSmemBytes = 1024 + kWsStages * kTcStageBytes + 128 + kWsEpiWarps * 32 * 33 * 4;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kWsThreads, 1) gemm_tc_ws_kernel(const __grid_constant__ GemmLaunch L, int groups) {
+  B200_PDL_PROLOGUE();
+  constexpr bool A_KM = (MODE != kWgrad);
+  constexpr bool B_KM = (MODE == kFwd);
+  extern __shared__ __align__(16) unsigned char tc_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kWsStages * kTcStageBytes);
+  uint64_t* empty = full + kWsStages;
+  uint64_t* acc_full = empty + kWsStages;
+  uint64_t* acc_empty = acc_full + 2;
+  float* epi = reinterpret_cast<float*>(smem + kWsStages * kTcStageBytes + 128);
+  __shared__ uint32_t s_tmem_base;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  if (tid == 32) {
+    for (int s = 0; s < kWsStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], kWsEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+  const int total_items = L.total_tiles * groups;
+
+  // work item -> (seed, problem, first row)
+  auto decode = [&](int item, int& g, int& pi, int& i0) {
+    g = item / L.total_tiles;
+    const int tile = item - g * L.total_tiles;
+    pi = 0;
+    while (pi + 1 < L.nprob && tile >= L.p[pi + 1].tile_begin) ++pi;
+    i0 = (tile - L.p[pi].tile_begin) * kTcM;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---- TMA producer
+      unsigned it = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        int g, pi, i0;
+        decode(item, g, pi, i0);
+        const GemmProblem& sp = L.p[pi];
+        const unsigned char* maps = reinterpret_cast<const unsigned char*>(L.tmaps) + (size_t)pi * 6 * kTmapBytes;
+        const uint32_t tx_bytes = (uint32_t)(kTcM * 128 + sp.J * 128);
+        for (int sg = 0; sg < sp.nseg; ++sg) {
+          for (int r0 = 0; r0 < sp.seg[sg].len; r0 += kTcBK, ++it) {
+            const unsigned s = it % kWsStages, use = it / kWsStages;
+            if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+            unsigned char* At = smem + s * kTcStageBytes;
+            mbar_expect_tx(&full[s], tx_bytes);
+            if (A_KM) tma_load_3d(At, maps + (sg * 2 + 0) * kTmapBytes, r0, i0, g, &full[s]);
+            else tma_load_4d(At, maps + (sg * 2 + 0) * kTmapBytes, 0, r0, i0 / 32, g, &full[s]);
+            if (B_KM) tma_load_3d(At + kTcATileBytes, maps + (sg * 2 + 1) * kTmapBytes, r0, 0, g, &full[s]);
+            else tma_load_4d(At + kTcATileBytes, maps + (sg * 2 + 1) * kTmapBytes, 0, r0, 0, g, &full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---- MMA issuer
+      const uint32_t smem_base_u32 = smem_u32(smem);
+      unsigned it = 0, n = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
+        int g, pi, i0;
+        decode(item, g, pi, i0);
+        const GemmProblem& sp = L.p[pi];
+        const uint32_t idesc = tc_instr_desc((sp.J + 15) & ~15, !A_KM, !B_KM);
+        const unsigned a = n & 1, ause = n >> 1;
+        if (ause > 0) mbar_wait(&acc_empty[a], (ause - 1) & 1);  // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + a * 256u;
+        int c = 0;
+        for (int sg = 0; sg < sp.nseg; ++sg) {
+          for (int r0 = 0; r0 < sp.seg[sg].len; r0 += kTcBK, ++it, ++c) {
+            const unsigned s = it % kWsStages, use = it / kWsStages;
+            mbar_wait(&full[s], use & 1);
+            tc_fence_after();
+            const uint32_t a_addr = smem_base_u32 + s * kTcStageBytes;
+            const uint32_t b_addr = a_addr + kTcATileBytes;
+#pragma unroll
+            for (int kk = 0; kk < kTcBK / 8; ++kk) {
+              const uint64_t da = A_KM ? tc_smem_desc(a_addr + kk * 32, 16, 1024, 2) : tc_smem_desc(a_addr + kk * 1024, 4096, 512, 1);
+              const uint64_t db = B_KM ? tc_smem_desc(b_addr + kk * 32, 16, 1024, 2) : tc_smem_desc(b_addr + kk * 1024, 4096, 512, 1);
+              tc_mma_tf32(tmem_acc, da, db, idesc, (c > 0 || kk > 0) ? 1u : 0u);
+            }
+            tc_commit(&empty[s]);
+          }
+        }
+        tc_commit(&acc_full[a]);
+      }
+    }
+  } else if (warp >= 4) {  // ---- epilogue warps
+    const int ew = warp - 4;
+    float* st = epi + ew * (32 * 33);
+    unsigned n = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
+      int g, pi, i0;
+      decode(item, g, pi, i0);
+      const GemmProblem& sp = L.p[pi];
+      const unsigned a = n & 1, ause = n >> 1;
+      mbar_wait(&acc_full[a], ause & 1);
+      tc_fence_after();
+      constexpr int kColsPerWarp = 256 / (kWsEpiWarps / 4);
+      tc_epilogue_warp<MODE>(sp, g, sp.I, sp.J, (sp.J + 15) & ~15, i0, warp & 3, (ew >> 2) * kColsPerWarp, st, lane, tmem_base + a * 256u, 1, kColsPerWarp / 32);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[a]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 

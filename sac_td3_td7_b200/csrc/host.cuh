@@ -213,6 +213,7 @@ inline int gemm_table_upload(GemmTable* t, int mode, std::vector<GemmProblem>& p
   t->groups = groups;
   memset(&t->launch, 0, sizeof(t->launch));
   memset(&t->launch_tc, 0, sizeof(t->launch_tc));
+  memset(&t->launch_ws, 0, sizeof(t->launch_ws));
   if (const char* e = getenv("B200RL_SPLITK")) force_splitk = atoi(e);  // tuning knob (profiles/sweep_gemm.py)
   int splitk = ff.empty() ? 1 : (force_splitk > 0 ? force_splitk : choose_splitk(ff, tiles, groups));
 #ifdef B200_EMU
@@ -259,7 +260,38 @@ inline int gemm_table_upload(GemmTable* t, int mode, std::vector<GemmProblem>& p
       }
       if (ok) mask |= 1u << i;
     }
-    if (mask) {
+    static const bool use_ws = [] { const char* e = getenv("B200RL_TC_WS"); return e ? atoi(e) != 0 : true; }();  // B200RL_TC_WS=0: one tile per CTA
+    if (mask && use_ws) {
+      // the TMA-addressable problems move to the persistent warp-specialised kernel; the rest stay where they are
+      std::vector<GemmProblem> ws, rest;
+      std::vector<CUtensorMap> ws_maps;
+      for (size_t i = 0; i < tc.size(); ++i) {
+        if ((mask >> i) & 1u) {
+          ws.push_back(tc[i]);
+          for (int q = 0; q < 6; ++q) ws_maps.push_back(maps[i * 6 + q]);
+        } else {
+          rest.push_back(tc[i]);
+        }
+      }
+      int wt = 0;
+      for (auto& p : ws) { p.tile_begin = wt; wt += p.I / kTcM; }
+      int rt = 0;
+      for (auto& p : rest) { p.tile_begin = rt; rt += p.I / kTcM; }
+      CUtensorMap* d_maps = nullptr;
+      B200_TRY(arena->alloc(&d_maps, ws_maps.size()));
+      B200_CHECK_CUDA(cudaMemcpy(d_maps, ws_maps.data(), ws_maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+      memset(&t->launch_ws, 0, sizeof(t->launch_ws));
+      for (size_t i = 0; i < ws.size(); ++i) t->launch_ws.p[i] = ws[i];
+      t->launch_ws.nprob = (int)ws.size();
+      t->launch_ws.total_tiles = wt;
+      t->launch_ws.tmaps = d_maps;
+      t->launch_ws.tma_mask = (1u << ws.size()) - 1u;
+      memset(&t->launch_tc, 0, sizeof(t->launch_tc));
+      for (size_t i = 0; i < rest.size(); ++i) t->launch_tc.p[i] = rest[i];
+      t->launch_tc.nprob = (int)rest.size();
+      tct = rt;
+      t->tc_tiles = rt;
+    } else if (mask) {
       CUtensorMap* d_maps = nullptr;
       B200_TRY(arena->alloc(&d_maps, maps.size()));
       B200_CHECK_CUDA(cudaMemcpy(d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
@@ -288,6 +320,24 @@ inline int gemm_table_launch(const GemmTable& t, int groups, cudaStream_t stream
     B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kDgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
     B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<kWgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
     attr_set = true;
+  }
+  if (t.launch_ws.nprob > 0) {
+    static const int n_sm = [] { int v = 148, d = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
+    static bool ws_attr = false;
+    if (!ws_attr) {
+      B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_ws_kernel<kFwd>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes));
+      B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_ws_kernel<kDgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes));
+      B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_ws_kernel<kWgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWsSmemBytes));
+      ws_attr = true;
+    }
+    const int items = t.launch_ws.total_tiles * groups;
+    dim3 grid((unsigned)std::min(items, n_sm), 1, 1), block(kWsThreads, 1, 1);
+    switch (t.mode) {
+      case kFwd: { auto k = gemm_tc_ws_kernel<kFwd>; B200_LAUNCH(k, grid, block, kWsSmemBytes, stream, t.launch_ws, groups); break; }
+      case kDgrad: { auto k = gemm_tc_ws_kernel<kDgrad>; B200_LAUNCH(k, grid, block, kWsSmemBytes, stream, t.launch_ws, groups); break; }
+      default: { auto k = gemm_tc_ws_kernel<kWgrad>; B200_LAUNCH(k, grid, block, kWsSmemBytes, stream, t.launch_ws, groups); break; }
+    }
+    B200_CHECK_LAUNCH();
   }
   if (t.launch_tc.nprob > 0) {
     dim3 grid((unsigned)t.tc_tiles, (unsigned)groups, 1), block(kTcThreads, 1, 1);
