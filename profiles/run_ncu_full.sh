@@ -13,3 +13,10 @@ case "$1" in
     python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:lap_sample_kernel -s 10 -c 1 -o gpurun_out/prof_lap_sample_r01 -f python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/ncu.log 2>&1
     tail -1 gpurun_out/plain.log | cut -c1-200 ;;
 esac
+# persistent warp-specialised tcgen05 kernel: bash profiles/run_ncu_full.sh ws0 | ws2
+case "$1" in
+  ws0|ws2)
+    export ITERS=4 MODE=${1#ws}
+    python profiles/prof_gemm_tc.py > gpurun_out/prof_ws${MODE}_plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:gemm_tc_ws -s 3 -c 1 -o gpurun_out/prof_gemm_tc_ws_mode${MODE}_r01 -f python profiles/prof_gemm_tc.py > gpurun_out/prof_ws${MODE}_ncu.log 2>&1
+    tail -1 gpurun_out/prof_ws${MODE}_plain.log ;;
+esac

@@ -7,15 +7,20 @@
 //   * operands stay fp32 in HBM/L2 and are consumed as TF32 (`kind::tf32`, 10-bit mantissa, fp32
 //     accumulate) -- the north star's "stated TF32 tolerance" applies to the stacked path only; the
 //     single-agent path stays fp32 FFMA,
-//   * 32-deep (128-byte) reduction chunks are staged by cp.async straight into the canonical UMMA
-//     SWIZZLE_128B shared-memory layouts (K-major for operands contiguous along the reduction,
-//     MN-major otherwise, so forward / dgrad / wgrad need no transposed copies), 2 stages x 48 KB so two
-//     CTAs share an SM and one CTA's epilogue overlaps the other's main loop,
+//   * 32-deep (128-byte) reduction chunks land straight in the canonical UMMA SWIZZLE_128B shared-memory
+//     layouts (K-major for operands contiguous along the reduction, MN-major otherwise, so forward /
+//     dgrad / wgrad need no transposed copies) -- by TMA (cp.async.bulk.tensor, 3-D / 4-D tensor maps
+//     built on the host, one issuing thread) wherever the operand's base and row stride are 16-byte
+//     aligned, else by per-thread cp.async,
 //   * one elected thread issues 4 x tcgen05.mma (M=128, N, K=8) per chunk and commits to an mbarrier
 //     that frees the stage; the epilogue reads TMEM with tcgen05.ld (32 lanes x 32 columns per warp)
 //     and applies the same fused epilogues as the FFMA kernel (bias+activation(+noise), act', Adam).
+// Two kernels share this machinery: gemm_tc_kernel (one tile per CTA, 2 stages x 48 KB so two CTAs share
+// an SM and one CTA's epilogue overlaps the other's main loop; cp.async or TMA), and gemm_tc_ws_kernel
+// (persistent, warp-specialised: TMA producer warp, MMA warp, two TMEM accumulators, sixteen epilogue
+// warps; TMA-addressable problems only -- the default for them).
 // Eligibility (host): rows multiple of 128, 64 <= N <= 256 and N % 16 == 0; everything else in a table
-// (action-width layers, bias gradients) stays on the FFMA kernel in the same phase.
+// (action-width layers) stays on the FFMA kernel in the same phase, bias gradients go to bias_grad_kernel.
 #pragma once
 #ifndef B200_EMU
 #include "gemm.cuh"
