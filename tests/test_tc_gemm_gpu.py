@@ -128,3 +128,19 @@ def test_tc_stacked_groups_and_mixed_table(tc):
     refa = torch.tanh(torch.einsum("gmk,gnk->gmn", torch.tensor(x), torch.tensor(Wa))).numpy()
     assert nerr(dev.from_dev(y, (G, M, N)), ref) < TOL
     assert nerr(dev.from_dev(ya, (G, M, A)), refa) < 2e-6  # fp32 FFMA path
+
+
+@pytest.mark.parametrize("env", [{"B200RL_TC_WS": "0"}, {"B200RL_TC_TMA": "0"}])
+def test_tc_kernel_variants_in_a_fresh_process(env):
+    """The kernel variant is chosen once per process (persistent warp-specialised + TMA by default): run this module's
+    other tests again with the one-tile-per-CTA TMA kernel, and with the cp.async staging, each in its own process."""
+    import os
+    import subprocess
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    e = dict(os.environ, **env)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_tc_gemm_gpu.py"), "-q", "-x", "-m", "gpu", "-k", "not fresh_process",
+                        "-p", "no:cacheprovider"], env=e, capture_output=True, text=True, timeout=600, cwd=os.path.dirname(here))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
