@@ -48,6 +48,45 @@ __global__ void __launch_bounds__(256) avgl1norm_kernel(const RowOp* __restrict_
   float s_abs = 0.f, s_dot = 0.f;
   const float* dy = nullptr;
   if (BWD) dy = op.dy + (long long)g * op.dy_gs + (long long)row * op.dy_ld;
+  // 128-bit path: rows of up to 512 floats whose base addresses are 16-byte aligned (the 256-wide SALE layers) are
+  // held in registers -- every load of the row is in flight at once and the row is read from memory only once
+  const bool vec = (n % 128 == 0) && n <= 512 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | (BWD ? reinterpret_cast<uintptr_t>(dy) : 0)) & 15) == 0;
+  if (vec) {
+    const int nv = n >> 7;  // float4 per lane
+    float4 xv[4], dv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < nv) {
+        xv[k] = *reinterpret_cast<const float4*>(x + k * 128 + lane * 4);
+        if (BWD) dv[k] = *reinterpret_cast<const float4*>(dy + k * 128 + lane * 4);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < nv) {
+        s_abs += (fabsf(xv[k].x) + fabsf(xv[k].y)) + (fabsf(xv[k].z) + fabsf(xv[k].w));
+        if (BWD) s_dot = fmaf(dv[k].x, xv[k].x, fmaf(dv[k].y, xv[k].y, fmaf(dv[k].z, xv[k].z, fmaf(dv[k].w, xv[k].w, s_dot))));
+      }
+    }
+    s_abs = warp_sum(s_abs);
+    const float mean = s_abs / (float)n;
+    const float c = fmaxf(mean, kNormEps);
+    if (!BWD) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k < nv) *reinterpret_cast<float4*>(y + k * 128 + lane * 4) = make_float4(xv[k].x / c, xv[k].y / c, xv[k].z / c, xv[k].w / c);
+    } else {
+      s_dot = warp_sum(s_dot);
+      const float gm = (mean >= kNormEps) ? (-s_dot / (c * c)) / (float)n : 0.f;
+      auto sgn = [](float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); };
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k < nv)
+          *reinterpret_cast<float4*>(y + k * 128 + lane * 4) = make_float4(dv[k].x / c + sgn(xv[k].x) * gm, dv[k].y / c + sgn(xv[k].y) * gm,
+                                                                            dv[k].z / c + sgn(xv[k].z) * gm, dv[k].w / c + sgn(xv[k].w) * gm);
+    }
+    return;
+  }
   for (int j = lane; j < n; j += 32) {
     float v = x[j];
     s_abs += fabsf(v);
