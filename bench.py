@@ -326,6 +326,17 @@ def run_gpu_arm(args):
                  "full_rebuild_kernel": {"kernel": "lap_tile_sums_kernel (bulk loads / restored checkpoints only)", "launch_ms": ms2[0], "bytes_per_launch": bytes_scan,
                                          "achieved_gbs": bytes_scan / (ms2[0] * 1e-3) / 1e9}}
 
+    roof3 = None
+    if seeds >= 8:  # stacked seeds: the tcgen05 kernels (HBM- and tensor-side figures)
+        roof3 = {}
+        for mode, name in ((0, "forward"), (2, "wgrad_adam")):
+            fl, by, ms3 = stacked_roofline(lib, torch, seeds, mode)
+            roof3[name] = {"kernel": "gemm_tc_ws_kernel (persistent tcgen05 TF32, TMA-fed), 2 layers x %d seeds" % seeds, "launch_ms": ms3,
+                           "hbm": {"achieved": by / (ms3 * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": by / (ms3 * 1e-3) / 1e9 / hbm_peak},
+                           "tensor": {"achieved": fl / (ms3 * 1e-3) / 1e12, "peak": bf16_sus, "unit": "TFLOP/s", "frac": fl / (ms3 * 1e-3) / 1e12 / bf16_sus,
+                                      "note": "TF32 issue rate is half of bf16; the stacked update is HBM-bound at B=256 per seed"},
+                           "bytes_per_launch": by, "flops_per_launch": fl, "peak_source": peak_src}
+
     # ---- CPU baseline (oracle port) on this host, bounded ----
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -344,7 +355,7 @@ def run_gpu_arm(args):
                    "replay": "LAP" if prio else "uniform", "seeds_per_gpu": seeds, "parallelism": f"replicas x{world} (independent agents, no data-path collective)",
                    "l2": "replay rows exceed L2 (1M rows); weights, Adam moments and the 4 MB priority array are L2-resident by design -- they are the loop state"},
         "e2e": e2e, "gpu_launches": int(K * (per_update + 1)), "launches_per_update": {"critic_only": lp0, "with_actor": lp1},
-        "clocks": clk, "roofline": roofline, "roofline_replay": roof2, "cpu_baseline": cpu,
+        "clocks": clk, "roofline": roofline, "roofline_replay": roof2, "roofline_stacked": roof3, "cpu_baseline": cpu,
         "algorithmic_gflop_per_update": gflop, "update_tflops_per_gpu": gflop * value / 1e3 / world,
         "last_info": last,
     }
@@ -353,6 +364,44 @@ def run_gpu_arm(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def stacked_roofline(lib, torch, G, mode):
+    """Graph-timed launch of the tcgen05 grouped GEMM on `G` stacked seeds: two 256x256x256 layers (mode 0: forward +
+    bias + ELU; mode 2: weight gradient + fused Adam).  Returns (flops, algorithmic bytes, ms per launch)."""
+    from sac_td3_td7_b200 import _lib
+
+    os.environ.setdefault("B200RL_TC", "1")
+    dev = torch.device("cuda")
+    Bn, H, K = 256, 256, 256
+    keep, probs = [], []
+    for _ in range(2):
+        p = _lib.GemmProblem()
+        if mode == 0:
+            x, w = torch.randn(G, Bn, K, device=dev), torch.randn(G, H, K, device=dev) / 16
+            b, y = torch.randn(G, H, device=dev), torch.empty(G, Bn, H, device=dev)
+            p.I, p.J, p.C, p.c_ld, p.c_gs, p.act, p.bias, p.bias_gs = Bn, H, y.data_ptr(), H, Bn * H, 2, b.data_ptr(), H
+            sg = p.seg[0]
+            sg.A, sg.a_ld, sg.a_gs, sg.B, sg.b_ld, sg.b_gs, sg.len = x.data_ptr(), K, Bn * K, w.data_ptr(), K, H * K, K
+            keep += [x, w, b, y]
+        else:
+            dz, x = torch.randn(G, Bn, H, device=dev) / Bn, torch.randn(G, Bn, K, device=dev)
+            w, m, v = torch.randn(G, H, K, device=dev) / 16, torch.zeros(G, H, K, device=dev), torch.zeros(G, H, K, device=dev)
+            sc = _lib.AdamScalars(w1=0.1, beta2=0.999, w2=0.001, bc2_sqrt=0.0316, neg_step=-3e-3, eps=1e-8, step=1)
+            scd = torch.frombuffer(bytearray(bytes(sc)), dtype=torch.uint8).to(dev)
+            p.I, p.J, p.c_ld = H, K, K
+            p.P, p.M, p.V, p.p_ld, p.p_gs, p.adam = w.data_ptr(), m.data_ptr(), v.data_ptr(), K, H * K, scd.data_ptr()
+            sg = p.seg[0]
+            sg.A, sg.a_ld, sg.a_gs, sg.B, sg.b_ld, sg.b_gs, sg.len = dz.data_ptr(), H, Bn * H, x.data_ptr(), K, Bn * K, Bn
+            keep += [dz, x, w, m, v, scd]
+        p.nseg = 1
+        probs.append(p)
+    arr = (_lib.GemmProblem * 2)(*probs)
+    ms = C.c_float()
+    _lib.check(lib.b200rl_op_gemm_timed(mode, arr, 2, G, 3, 20, C.byref(ms), torch.cuda.current_stream().cuda_stream))
+    flops = 2 * 2.0 * G * Bn * H * K
+    byts = 2 * G * 4.0 * (Bn * K + H * K + Bn * H) if mode == 0 else 2 * G * 4.0 * (Bn * H + Bn * K + 6 * H * K)
+    return flops, byts, ms.value
 
 
 def main():
