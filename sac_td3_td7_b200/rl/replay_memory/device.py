@@ -88,7 +88,12 @@ class _DeviceRing(BaseReplayMemory):
         self.append_rows(row, seed)
 
     def append_rows(self, rows, seed: int = 0) -> None:
-        """Bulk append of packed rows (numpy / CPU tensor -> H2D, CUDA tensor -> D2D)."""
+        """Bulk append of packed rows (numpy / CPU tensor -> H2D, CUDA tensor -> D2D).
+
+        Up to 64 rows whose memory the GPU can read directly -- CUDA tensors, or numpy views of PINNED host memory --
+        are appended by one kernel that reads the source when it executes, in stream order (like cudaMemcpyAsync from
+        pinned memory: keep such a source unchanged until then, e.g. rotate a few pinned slots).  Pageable rows are
+        staged by the driver at call time and may be reused immediately."""
         if isinstance(rows, torch.Tensor) and rows.is_cuda:
             rows = rows.contiguous().float()
             _lib.check(self._lib.b200rl_replay_append_device(self._h, seed, rows.data_ptr(), rows.shape[0], _stream()))
