@@ -298,6 +298,9 @@ struct TD7Agent : AgentBase {
     B200_TRY(fork.link(M, sP));
     B200_TRY(launch_prep(actor ? 0x7u : 0x6u, sP));  // optimizers: 0 policy, 1 critics, 2 encoder
     B200_TRY(launch_gauss(noise, 0, sP));
+    // ---- critic chain: its first launch (4 x 64 tiles) gets the machine to itself; the encoder branch, which has slack,
+    // forks off behind it instead of competing for the first wave of CTAs
+    GL(C[0], M);
     // ---- encoder branch
     B200_TRY(fork.link(M, sE));
     GL(E[0], sE); GL(E[1], sE); GL(E[2], sE); RL(En[0], sE);
@@ -306,8 +309,6 @@ struct TD7Agent : AgentBase {
     B200_TRY(launch_enc_loss(sE));
     GL(E[6], sE); GL(We[5], sE); GL(E[7], sE); GL(We[4], sE); GL(E[8], sE); GL(We[3], sE); RL(En[1], sE);
     GL(E[9], sE); GL(We[2], sE); GL(E[10], sE); GL(We[1], sE); GL(We[0], sE);
-    // ---- critic chain
-    GL(C[0], M);
     B200_TRY(fork.link(M, sN));
     RL(CnQ, sN);
     GL(C2v[actor ? 1 : 0], M);

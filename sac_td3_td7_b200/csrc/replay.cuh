@@ -209,7 +209,57 @@ __device__ __forceinline__ int warp_first_reaching(const double (&x)[K], double 
   return src * K + kk;
 }
 
-__global__ void __launch_bounds__(256) lap_sample_kernel(SampleArgs a) {
+// One warp copies `len` floats of a replay row (read-only for the whole launch: ld.global.nc) to a batch tensor row.
+// Every load of a batch is issued before the first store so a lane keeps up to four 16-byte requests in flight;
+// a 16-byte aligned destination gets 128-bit stores (the source side then reads 128-bit when it is aligned too, else
+// four 32-bit loads of the same sectors), anything else goes lane-per-float, coalesced on both sides.
+__device__ __forceinline__ void warp_copy_row_segment(float* __restrict__ dst, const float* __restrict__ src, int len, int lane) {
+  if ((reinterpret_cast<unsigned long long>(dst) & 15ull) == 0ull && len >= 64) {
+    const int n4 = len >> 2;
+    const bool src_al = (reinterpret_cast<unsigned long long>(src) & 15ull) == 0ull;
+    for (int q0 = 0; q0 < n4; q0 += 128) {
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = q0 + j * 32 + lane;
+        if (q < n4) {
+          if (src_al) {
+            v[j] = __ldg(reinterpret_cast<const float4*>(src) + q);
+          } else {
+            v[j].x = __ldg(src + 4 * q);
+            v[j].y = __ldg(src + 4 * q + 1);
+            v[j].z = __ldg(src + 4 * q + 2);
+            v[j].w = __ldg(src + 4 * q + 3);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = q0 + j * 32 + lane;
+        if (q < n4) reinterpret_cast<float4*>(dst)[q] = v[j];
+      }
+    }
+    const int i = n4 * 4 + lane;
+    if (i < len) dst[i] = __ldg(src + i);
+    return;
+  }
+  for (int i0 = 0; i0 < len; i0 += 128) {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + j * 32 + lane;
+      if (i < len) v[j] = __ldg(src + i);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + j * 32 + lane;
+      if (i < len) dst[i] = v[j];
+    }
+  }
+}
+
+template <int kMinCtas>
+__global__ void __launch_bounds__(256, kMinCtas) lap_sample_kernel(SampleArgs a) {
   B200_PDL_PROLOGUE();
   const int g = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -235,18 +285,37 @@ __global__ void __launch_bounds__(256) lap_sample_kernel(SampleArgs a) {
     const int nsup = a.nsuper;
     const int per = (nsup + 31) >> 5;
     const int s_lo = min(lane * per, nsup), s_hi = min(s_lo + per, nsup);
+    // one pass over the super sums: up to 4 per lane stay in registers (capacities up to 2 M rows); beyond that the
+    // second loop reads them again
+    double sv[4] = {0.0, 0.0, 0.0, 0.0};
     double run = 0.0;
-    for (int t = s_lo; t < s_hi; ++t) run += ld_cgd(ss + t);
+    if (per <= 4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (s_lo + k < s_hi) sv[k] = ld_cgd(ss + s_lo + k);
+      run = ((sv[0] + sv[1]) + sv[2]) + sv[3];
+    } else {
+      for (int t = s_lo; t < s_hi; ++t) run += ld_cgd(ss + t);
+    }
     const double incl = warp_inclusive_scan(run, lane);
     const double total = shfl_double(incl, 31);
     const float v = __fmul_rn(u, (float)total);
     double acc = incl - run;  // exclusive prefix of this lane's run
     int sfirst = -1;
     double sbase = 0.0;
-    for (int t = s_lo; t < s_hi; ++t) {
-      const double nx = acc + ld_cgd(ss + t);
-      if (sfirst < 0 && (float)nx >= v) { sfirst = t; sbase = acc; }
-      acc = nx;
+    if (per <= 4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const double nx = acc + sv[k];
+        if (sfirst < 0 && s_lo + k < s_hi && (float)nx >= v) { sfirst = s_lo + k; sbase = acc; }
+        acc = nx;
+      }
+    } else {
+      for (int t = s_lo; t < s_hi; ++t) {
+        const double nx = acc + ld_cgd(ss + t);
+        if (sfirst < 0 && (float)nx >= v) { sfirst = t; sbase = acc; }
+        acc = nx;
+      }
     }
     const unsigned shit = __ballot_sync(0xffffffffu, sfirst >= 0);
     int sup = nsup - 1;
@@ -284,27 +353,16 @@ __global__ void __launch_bounds__(256) lap_sample_kernel(SampleArgs a) {
   }
   if (lane == 0 && a.idx_out) a.idx_out[(long long)g * a.idx_gs + b] = idx;
 
-  // ---- gather the packed row with 128-bit loads, scatter into the five batch tensors ----
+  // ---- gather the packed row into the five batch tensors ----
   const float* row = a.rows + (long long)g * a.rows_gs + idx * (long long)a.row_stride;
   const int S = a.S, A = a.A;
-  const int o_act = S, o_rew = S + A, o_done = S + A + 1, o_next = S + A + 2, o_end = 2 * S + A + 2;
-  float* st = a.state + (long long)g * a.state_gs + (long long)b * a.ld_state;
-  float* ac = a.action + (long long)g * a.action_gs + (long long)b * a.ld_action;
-  float* ns = a.next_state + (long long)g * a.next_gs + (long long)b * a.ld_next;
-  for (int q = lane; q * 4 < o_end; q += 32) {
-    const float4 v4 = *reinterpret_cast<const float4*>(row + q * 4);
-    const float vals[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int pos = q * 4 + k;
-      const float val = vals[k];
-      if (pos < o_act) st[pos] = val;
-      else if (pos < o_rew) ac[pos - o_act] = val;
-      else if (pos == o_rew) a.reward[(long long)g * a.reward_gs + b] = val;
-      else if (pos == o_done) a.done[(long long)g * a.done_gs + b] = val;
-      else if (pos < o_end) ns[pos - o_next] = val;
-    }
+  if (lane == 0) {
+    a.reward[(long long)g * a.reward_gs + b] = __ldg(row + S + A);
+    a.done[(long long)g * a.done_gs + b] = __ldg(row + S + A + 1);
   }
+  warp_copy_row_segment(a.state + (long long)g * a.state_gs + (long long)b * a.ld_state, row, S, lane);
+  warp_copy_row_segment(a.next_state + (long long)g * a.next_gs + (long long)b * a.ld_next, row + S + A + 2, S, lane);
+  warp_copy_row_segment(a.action + (long long)g * a.action_gs + (long long)b * a.ld_action, row + S, A, lane);
 }
 
 __global__ void __launch_bounds__(1024) lap_update_priority_kernel(float* __restrict__ priority, long long prio_gs, float* __restrict__ max_priority,
@@ -545,7 +603,12 @@ struct Replay {
     a.B = B;
     a.prioritized = prioritized ? 1 : 0;
     dim3 grid((unsigned)ceil_div(B, 8), (unsigned)groups), block(256);
-    B200_LAUNCH(lap_sample_kernel, grid, block, 0, stream, a);
+    // stacked seeds: thousands of latency-bound warps, so 32 registers (8 CTAs = 64 warps per SM) beat 40 (6 CTAs);
+    // a single agent's 32 CTAs keep the spill-free build.  B200RL_SAMPLE_OCC8=0|1 forces either.
+    static const int occ8_env = [] { const char* e = getenv("B200RL_SAMPLE_OCC8"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+    const bool occ8 = occ8_env >= 0 ? occ8_env == 1 : groups > 1;
+    if (occ8) { auto k = lap_sample_kernel<8>; B200_LAUNCH(k, grid, block, 0, stream, a); }
+    else { auto k = lap_sample_kernel<6>; B200_LAUNCH(k, grid, block, 0, stream, a); }
     B200_CHECK_LAUNCH();
     last_batch = B;
     return kOk;

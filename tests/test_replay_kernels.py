@@ -178,3 +178,27 @@ def test_stacked_seeds_share_rows_and_device_rng(dev):
     assert idx2.min() >= 0 and idx2.max() < cap
     assert not np.array_equal(idx2[0], idx2[1])
     dev.check(dev.lib.b200rl_replay_destroy(h))
+
+
+@pytest.mark.parametrize("dims", [(376, 17), (64, 6), (100, 8), (27, 8), (17, 6), (130, 2)])
+def test_row_gather_every_width(dev, dims):
+    """The gather has a 128-bit path (16-byte aligned batch rows of >= 64 floats, with aligned and unaligned sources)
+    and a lane-per-float path: every env shape of BASELINE.json plus widths that land on each branch, all four
+    destination alignments (batch rows of odd width start at every offset mod 16 bytes), bit-exact, stacked seeds."""
+    s, a = dims
+    cap, G, B = 700, 2, 67
+    h = dev.replay_create(cap, s, a, groups=G, share_rows=True)
+    rows = oreplay.synthetic_rows(cap, s, a, seed=s)
+    packed = dev.pack_rows(h, rows["state"], rows["action"], rows["reward"], rows["next_state"], rows["done"])
+    for g in range(G):
+        dev.replay_append(h, packed, g)
+    pri = np.random.default_rng(s).uniform(1.0, 9.0, (G, cap)).astype(np.float32)
+    for g in range(G):
+        dev.replay_write_priority(h, pri[g], group=g)
+    u = np.random.default_rng(a).random((G, B), dtype=np.float32)
+    idx, batch, _ = dev.replay_sample(h, B, s, a, u=u, groups=G)
+    for g in range(G):
+        assert np.array_equal(idx[g], oreplay.sample_indices_numpy(pri[g], u[g]))
+        for k in ("state", "action", "reward", "next_state", "done"):
+            assert np.array_equal(batch[k][g], rows[k][idx[g]]), (dims, g, k)
+    dev.check(dev.lib.b200rl_replay_destroy(h))
