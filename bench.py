@@ -101,12 +101,18 @@ def run_reference_arm(args):
         return
     import torch
 
-    ups, n, el, threads = cpu_updates_per_s(args.workload, budget_s=20.0, steps=args.steps if args.steps_given else None, warmup=max(args.warmup, 3))
+    # A reference-arm step is a bounded sample of the workload: `per_step` consecutive updates, sized so that K steps hold
+    # at least ~600 updates (8-10 s of CPU work; a handful of 14 ms updates would time thread wake-ups, not the loop) and
+    # the whole run stays under a few minutes.  The default run (no --steps) is a 20 s sample.
+    warm = max(args.warmup, 10)
+    per_step = max(1, -(-600 // args.steps)) if args.steps_given else 1
+    ups, n, el, threads = cpu_updates_per_s(args.workload, budget_s=20.0, steps=args.steps * per_step if args.steps_given else None, warmup=warm)
     algo, env, prio, seeds, rows = WORKLOADS[args.workload]
+    k_steps = args.steps if args.steps_given else n
     line = {
         "impl": "reference", "metric": "gradient updates/sec (batch 256) per agent", "value": ups, "unit": "updates/s", "n_gpus": args.gpus,
-        "steps": n, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 / ups, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "steps": k_steps, "updates_per_step": n / k_steps, "warmup": warm, "ms_per_step": 1e3 * el / k_steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "algo": algo, "env": env, "batch": BATCH, "buffer_rows": rows, "replay": "LAP" if prio else "uniform"},
         "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": threads, "kind": "port",
                          "sample": f"{n} updates of the oracle port (torch {torch.__version__} CPU, {threads} threads, os.cpu_count={os.cpu_count()}) in {el:.1f}s"},
@@ -117,7 +123,7 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 class ClockSampler:
-    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    FIELDS = "timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
@@ -127,7 +133,12 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             self.p = None
 
-    def stop(self):
+    def stop(self, timed=None):
+        """Median SM clock and the throttle reasons seen.  `timed` = (t0, t1) wall-clock bounds of the timed region: its
+        samples are the ones reported; when the region is shorter than the 100 ms sampling period and holds none, the
+        samples of the whole loaded window (warm-up + timed + end-to-end loop) are reported instead, and `window` says so."""
+        import datetime
+
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -137,23 +148,30 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for ln in self.f.read().splitlines():
             parts = [x.strip() for x in ln.split(",")]
-            if len(parts) < 6:
+            if len(parts) < 7:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx = float(parts[1])
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                ts = -1.0  # unparsed time stamp: the sample still counts for the whole window
+            try:
+                rows.append((ts, float(parts[1]), float(parts[2]), [nm for nm, v in zip(names, parts[3:7]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, v in zip(names, parts[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
         os.unlink(self.f.name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        window = "warm-up + timed region + end-to-end loop"
+        if timed is not None:
+            inside = [r for r in rows if timed[0] <= r[0] <= timed[1]]
+            if inside:
+                rows, window = inside, "timed region"
+        sm = sorted(r[1] for r in rows)
+        mx = rows[-1][2] if rows else None
+        reasons = {nm for r in rows for nm in r[3]}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def measured_peaks():
@@ -237,20 +255,21 @@ def run_gpu_arm(args):
     stream = torch.cuda.current_stream()
 
     # ---- device-resident throughput: K updates through the burst API ----
+    clocks = ClockSampler(local) if rank == 0 else None
     agent.train_ops_n(W, buf)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    wall0 = time.time()
     e0.record(stream)
     infos = agent.train_ops_n(K, buf)
     e1.record(stream)
     torch.cuda.synchronize()
+    wall1 = time.time()
     ms = e0.elapsed_time(e1)
     last = {k: (None if v is None else float(v)) for k, v in infos[-1].items()}
-    clk = clocks.stop() if clocks else None
     t = torch.tensor([ms], device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -294,6 +313,7 @@ def run_gpu_arm(args):
                "note": "per step: append 1 transition from pinned host memory, sample(256), train_ops, float(info['train/q_fn']) -- the engine posts "
                        "every loss of the step to a pinned host mailbox the moment its kernel has run (8 B per value), so the read returns while "
                        "the step's backward pass is still executing and the next step's host calls overlap it; full sync at the end of the loop"}
+    clk = clocks.stop(timed=(wall0, wall1)) if clocks else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
