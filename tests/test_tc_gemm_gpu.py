@@ -144,3 +144,41 @@ def test_tc_kernel_variants_in_a_fresh_process(env):
                         "-p", "no:cacheprovider"], env=e, capture_output=True, text=True, timeout=600, cwd=os.path.dirname(here))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert " passed" in r.stdout
+
+
+@pytest.mark.parametrize("rows,out,dz_ld", [(256, 256, 256), (256, 256, 768), (130, 64, 64), (256, 6, 6), (67, 20, 24), (256, 1, 1)])
+def test_bias_gradient_column_sums(tc, rows, out, dz_ld):
+    """bias_grad_kernel (bias gradients of the tensor-core path): db = column sums of dZ as four chains over r mod 4
+    combined (s0 + s1) + (s2 + s3) -- the 128-bit path (out % 4 == 0, aligned) and the scalar path give that same fp32
+    sum bit for bit -- then fused Adam; stacked seeds."""
+    dev = tc
+    G = 3
+    rng = np.random.default_rng(rows + out)
+    dZ = rng.standard_normal((G, rows, dz_ld)).astype(np.float32)
+    b0 = rng.standard_normal((G, out)).astype(np.float32)
+    p_d, m_d, v_d, g_d = dev.to_dev(b0), dev.zeros(b0.shape), dev.zeros(b0.shape), dev.zeros(b0.shape)
+    sc = _lib.AdamScalars(w1=1 - 0.9, beta2=0.999, w2=1 - 0.999, bc2_sqrt=math.sqrt(1 - 0.999), neg_step=-(3e-4 / (1 - 0.9)), eps=1e-8, step=1)
+    q = _problem(out, 1, g_d, 1)
+    _seg(q, dev.to_dev(dZ), dz_ld, None, 0, rows, ones=1)
+    q.seg[0].a_gs, q.c_gs, q.p_gs = rows * dz_ld, out, out
+    q.P, q.M, q.V, q.p_ld, q.adam = p_d, m_d, v_d, 1, dev.to_dev(np.frombuffer(bytes(sc), np.uint8))
+    _run(dev, 2, [q], groups=G)
+    d = dZ[:, :, :out]
+    r4 = rows & ~3
+    chains = [d[:, k:r4:4, :] for k in range(4)]
+    s = []
+    for k in range(4):
+        acc = np.zeros((G, out), np.float32)
+        for r in range(chains[k].shape[1]):
+            acc = acc + chains[k][:, r, :]
+        s.append(acc)
+    for r in range(r4, rows):
+        s[0] = s[0] + d[:, r, :]
+    want = (s[0] + s[1]) + (s[2] + s[3])
+    g = dev.from_dev(g_d, b0.shape)
+    assert np.array_equal(g, want)
+    wt = torch.tensor(b0.copy(), requires_grad=True)
+    opt = torch.optim.Adam([wt], lr=3e-4)
+    wt.grad = torch.tensor(g)
+    opt.step()
+    assert np.abs(dev.from_dev(p_d, b0.shape) - wt.detach().numpy()).max() <= 2e-7
