@@ -202,3 +202,18 @@ def test_row_gather_every_width(dev, dims):
         for k in ("state", "action", "reward", "next_state", "done"):
             assert np.array_equal(batch[k][g], rows[k][idx[g]]), (dims, g, k)
     dev.check(dev.lib.b200rl_replay_destroy(h))
+
+
+def test_lap_sampling_beyond_two_million_rows(dev):
+    """More than 128 super-tiles (capacity > 2 M rows): a lane owns five or more super sums and takes the
+    re-reading branch of the top tree level instead of the register-resident one; indices bit-exact vs the oracle."""
+    n = 2_200_000
+    pri = (np.maximum(np.abs(np.random.default_rng(21).standard_normal(n) * 3), 1.0) ** 0.4).astype(np.float32)
+    u = np.random.default_rng(22).random(256, dtype=np.float32)
+    u[:3] = (0.0, 1.0 - 2.0 ** -24, 0.5)
+    h = dev.replay_create(n, 2, 1)
+    dev.replay_write_priority(h, pri)
+    dev.check(dev.lib.b200rl_replay_set_cursor(h, 0, 0, n))
+    idx, _, _ = dev.replay_sample(h, 256, 2, 1, u=u)
+    assert np.array_equal(idx[0], oreplay.sample_indices_numpy(pri, u))
+    dev.check(dev.lib.b200rl_replay_destroy(h))
