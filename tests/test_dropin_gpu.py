@@ -331,3 +331,32 @@ def test_stacked_population_on_tensor_cores():
     others = [pop.read_infos(1, steps, seed=g) for g in range(1, G)]
     for o in others:
         assert np.all(np.isfinite(o[:, :2])) and not np.allclose(o[:, :2], got0[:, :2])
+
+
+@pytest.mark.parametrize("algo", ["TD3", "SAC"])
+def test_stacked_mlp_population_on_tensor_cores(algo):
+    """TD3 / SAC populations (8 stacked seeds, uniform replay, shared rows) on the tcgen05 path: seed 0 shares weights,
+    transitions and Philox streams with a single fp32 agent and must track its critic loss within the TF32 tolerance;
+    the other seeds are distinct, finite learners."""
+    from sac_td3_td7_b200.rl import agent as bagent
+    from sac_td3_td7_b200.rl.replay_memory import SimpleReplayMemory
+
+    env, G, steps = "Walker2d-v4", 8, 8
+    cls = getattr(bagent, algo)
+    pop = cls(env, n_seeds=G)
+    pop.seed_population(700)
+    buf = SimpleReplayMemory(8192, env, n_seeds=G, share_rows=True)
+    buf.fill_synthetic(8192, seed=4)
+    torch.manual_seed(700)
+    one = cls(env)
+    b1 = SimpleReplayMemory(8192, env)
+    b1.fill_synthetic(8192, seed=4)
+    pop.train_ops_n(steps, buf)
+    one.train_ops_n(steps, b1)
+    ref = one.read_infos(1, steps)
+    got0 = pop.read_infos(1, steps, seed=0)
+    assert np.all(np.isfinite(got0[:, 0]))
+    assert np.abs(got0[:, 0] - ref[:, 0]).max() <= 2e-2 * np.abs(ref[:, 0]).max(), (got0[:, 0], ref[:, 0])
+    for g in range(1, G):
+        o = pop.read_infos(1, steps, seed=g)
+        assert np.all(np.isfinite(o[:, 0])) and not np.allclose(o[:, 0], got0[:, 0])
