@@ -35,6 +35,12 @@ int b200rl_version(void);
 /* 1 when built by nvcc for sm_100a, 0 for the test-only host emulation build */
 int b200rl_is_cuda_build(void);
 
+/* Product loop of the small-tile GEMM kernel (single agents, narrow layers): 0 = fp32 FFMA (default), 1 =
+ * error-compensated 3xTF32 on the warp-level tensor-core path (mma.sync), -1 = back to the default / B200RL_MMA.  Returns the previous
+ * setting.  Takes effect for launches recorded afterwards (update graphs already captured keep theirs).  A/B
+ * measurements and the parity tests of both paths. */
+int b200rl_set_mma(int on);
+
 /* ---- raw device memory helpers (tests, benches; Python normally uses torch tensors) ---- */
 int b200rl_malloc(void** out_dev, uint64_t bytes);
 int b200rl_free(void* dev);
@@ -60,6 +66,23 @@ int b200rl_replay_row_stride(const b200rl_replay* h);
  * priority = running max.  rows_host is host memory; *_device takes a device pointer. */
 int b200rl_replay_append(b200rl_replay* h, int group, const float* rows_host, int64_t count, void* stream);
 int b200rl_replay_append_device(b200rl_replay* h, int group, const float* rows_dev, int64_t count, void* stream);
+/* lap.py:35 `action = action / action_scale - action_bias` on the device: set the per-dimension scale / bias once
+ * (miscellaneous.py:58-66), then append rows whose action columns are still in ENVIRONMENT units.  The kernel divides
+ * and subtracts in IEEE fp32, which is what numpy computes for the fp32 actions the agents emit.  rows: <= 64 rows in
+ * pinned host memory or device memory (read by the kernel itself, in stream order). */
+int b200rl_replay_set_action_norm(b200rl_replay* h, const float* scale_host, const float* bias_host);
+int b200rl_replay_append_raw(b200rl_replay* h, int group, const float* rows, int64_t count, void* stream);
+/* one environment step of a whole population (rl/rollout.py:45 once per stacked seed) as ONE launch: `count` (<= 64)
+ * rows for every stacked seed, rows = [groups][count][row_stride] (private row stores) or [count][row_stride] (shared
+ * row store), pinned host or device memory; raw_actions != 0 normalises the action columns as above. */
+int b200rl_replay_append_all(b200rl_replay* h, const float* rows, int64_t count, int raw_actions, void* stream);
+/* rl/rollout.py:45 -> lap.py:31-43 for one environment step, straight from the caller's arrays: n = 1 (one transition
+ * for stacked seed `group`) or n = groups (one per stacked seed: obs [n][S], action [n][A], reward [n], next_obs [n][S],
+ * notdone [n]; a shared row store keeps seed 0's).  The library packs the row(s) into a pinned staging slot it owns
+ * (16 slots, one event each) and ONE kernel copies, normalises (raw_actions != 0), writes priorities and repairs the
+ * sum tree. */
+int b200rl_replay_append_transitions(b200rl_replay* h, int group, int n, const float* obs_host, const float* action_host, const float* reward_host,
+                                     const float* next_obs_host, const float* notdone_host, int raw_actions, void* stream);
 /* lap.py:45-64 (sample).  u_dev: [groups][B] uniforms in [0,1) or NULL (on-device Philox).
  * Outputs are [groups][B][dim] contiguous device tensors.  The sampled indices stay in the
  * handle for update_priority (lap.py:61); b200rl_replay_last_indices copies them out. */
@@ -114,6 +137,8 @@ int b200rl_agent_destroy(b200rl_agent* h);
 int b200rl_agent_net_count(const b200rl_agent* h);
 int b200rl_agent_net_info(const b200rl_agent* h, int net, int64_t* numel, int* nlayers);
 int b200rl_agent_layer_info(const b200rl_agent* h, int net, int layer, int64_t* w_off, int64_t* b_off, int* out_dim, int* in_dim, int* ld);
+/* group = -1 addresses every stacked seed at once: [groups][numel] contiguous (population checkpoints: one copy per
+ * tensor kind instead of one per seed); the TD7 value-range calls take group = -1 the same way ([groups][4]). */
 int b200rl_agent_read(b200rl_agent* h, int net, int which, int group, float* out_host, void* stream);
 int b200rl_agent_write(b200rl_agent* h, int net, int which, int group, const float* in_host, void* stream);
 /* td7.py:114-125 / td3.py:90-96 / sac.py:101-107 (load_state_dict(other_agent)); full=1 also copies
@@ -145,14 +170,20 @@ int b200rl_agent_update_n(b200rl_agent* h, b200rl_replay* replay, int n, void* s
 /* the info dict of update number `step` (1-based count of train_ops calls) while it is still in the
  * 1024-entry ring; columns: TD7 {train/encoder, train/q_fn, train/policy}; TD3 {train/q_fn,
  * train/policy, norm/policy}; SAC {train/q_fn, tmp, norm/tmp, train/policy, train/tmp, entropy}.
- * Synchronises `stream`. */
+ * Synchronises `stream`.  group = -1 reads every stacked seed: out_host [groups][count][cols]. */
 int b200rl_agent_info_cols(const b200rl_agent* h);
 int b200rl_agent_read_info(b200rl_agent* h, int64_t first_step, int count, int group, float* out_host, void* stream);
 /* acting forward of .sample() for one observation per stacked seed: obs_dev [groups][S] -> out_dev
  * [groups][A] (TD7/TD3: tanh policy output; SAC: [groups][2A] mean | raw log_std) --
  * td7.py:158-162, td3.py:137-141, sac.py:154-159 */
 int b200rl_agent_act(b200rl_agent* h, const float* obs_dev, float* out_dev, void* stream);
-/* parity probes of the last update: which = 0 q_target[B], 1 priority[B], 2 q1[B], 3 q2[B], 4 pi_action[B][A] */
+/* the same forward host to host (rl/rollout.py:42 -> td7.py:141-156): obs_host [groups][S] is copied into the engine's
+ * pinned slot, ONE kernel (a thread-block cluster per stacked seed) reads it over the bus, writes the action(s) into a
+ * pinned mailbox followed by a sequence tag, and the call returns as soon as the tag arrives -- no stream
+ * synchronisation, no copy-engine round trips.  out_host [groups][A] (SAC: [groups][2A]). */
+int b200rl_agent_act_host(b200rl_agent* h, const float* obs_host, float* out_host, void* stream);
+/* parity probes of the last update: which = 0 q_target[B], 1 priority[B], 2 q1[B], 3 q2[B], 4 pi_action[B][A],
+ * 5 the N(0,1) draws of the update [B][A] (target smoothing / SAC critic draw), 6 SAC's actor draw [B][A] */
 int b200rl_agent_debug_read(b200rl_agent* h, int which, int group, float* out_host, void* stream);
 /* the info value `col` of seed 0 for update `step` as soon as the kernel that computes it has run (it is posted to a
  * pinned host mailbox), without waiting for the rest of the update -- what `float(loss)` (td7.py:303,315,324) needs.

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200rl.so")
+# B200RL_LIB selects another build of the same sources (profiles/: the -DB200RL_PROBE timeline build)
+LIB_PATH = os.environ.get("B200RL_LIB") or os.path.join(_HERE, "libb200rl.so")
 
 c_f32p = C.POINTER(C.c_float)
 c_i64p = C.POINTER(C.c_int64)
@@ -67,6 +68,7 @@ SIGNATURES = {
     "b200rl_last_error": (C.c_char_p, []),
     "b200rl_version": (C.c_int, []),
     "b200rl_is_cuda_build": (C.c_int, []),
+    "b200rl_set_mma": (C.c_int, [C.c_int]),
     "b200rl_malloc": (C.c_int, [C.POINTER(c_vp), C.c_uint64]),
     "b200rl_free": (C.c_int, [c_vp]),
     "b200rl_memcpy_h2d": (C.c_int, [c_vp, c_vp, C.c_uint64, c_vp]),
@@ -78,6 +80,10 @@ SIGNATURES = {
     "b200rl_replay_row_stride": (C.c_int, [c_vp]),
     "b200rl_replay_append": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int64, c_vp]),
     "b200rl_replay_append_device": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int64, c_vp]),
+    "b200rl_replay_set_action_norm": (C.c_int, [c_vp, c_vp, c_vp]),
+    "b200rl_replay_append_raw": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int64, c_vp]),
+    "b200rl_replay_append_all": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int, c_vp]),
+    "b200rl_replay_append_transitions": (C.c_int, [c_vp, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, c_vp]),
     "b200rl_replay_sample": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b200rl_replay_last_indices": (C.c_int, [c_vp, c_vp, c_vp]),
     "b200rl_replay_update_priority": (C.c_int, [c_vp, c_vp, C.c_int, c_vp]),
@@ -112,6 +118,7 @@ SIGNATURES = {
     "b200rl_agent_wait_info": (C.c_int, [c_vp, C.c_int64, C.c_int, C.POINTER(C.c_float)]),
     "b200rl_agent_read_info": (C.c_int, [c_vp, C.c_int64, C.c_int, C.c_int, c_vp, c_vp]),
     "b200rl_agent_act": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "b200rl_agent_act_host": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "b200rl_agent_debug_read": (C.c_int, [c_vp, C.c_int, C.c_int, c_vp, c_vp]),
     "b200rl_agent_launches_per_update": (C.c_int, [c_vp, C.c_int]),
     # ops

@@ -39,6 +39,17 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(s) <= t for s in sources())
 
 
+def build_probe() -> str:
+    """Profiling build with the in-kernel timeline (-DB200RL_PROBE): libb200rl_probe.so, loaded with B200RL_LIB=..."""
+    out = os.path.join(HERE, "libb200rl_probe.so")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    res = subprocess.run([nvcc, *NVCC_FLAGS, "-DB200RL_PROBE", os.path.join(CSRC, "b200rl.cu"), "-o", out], capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed building the probe library")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return OUT
@@ -60,4 +71,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--probe" in sys.argv:
+        print(build_probe())
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

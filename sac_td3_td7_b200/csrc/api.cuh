@@ -6,6 +6,7 @@
 #include <memory>
 
 #include "../../include/b200rl.h"
+#include "act.cuh"
 #include "agent_mlp.cuh"
 #include "agent_td7.cuh"
 
@@ -34,6 +35,19 @@ struct b200rl_agent {
   GemmTable act_t[6];
   RowTable act_n[2];
   int n_act_t = 0;
+  // fused acting kernel (act.cuh) + its pinned host slots: observation in, action out, sequence tag
+  ActArgs act_args;
+  float* h_obs = nullptr; float* d_obs_map = nullptr;
+  float* h_act = nullptr; float* d_act_map = nullptr;
+  unsigned long long* h_tag = nullptr; unsigned long long* d_tag_map = nullptr;
+  unsigned* d_done = nullptr;
+  unsigned long long act_seq = 0;
+  int act_smem = 0;
+  ~b200rl_agent() {
+    if (h_obs) cudaFreeHost(h_obs);
+    if (h_act) cudaFreeHost(h_act);
+    if (h_tag) cudaFreeHost(h_tag);
+  }
 };
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -61,6 +75,12 @@ int b200rl_is_cuda_build(void) {
 #else
   return 1;
 #endif
+}
+
+int b200rl_set_mma(int on) {
+  const int prev = use_mma() ? 1 : 0;
+  mma_override() = on < 0 ? -1 : (on != 0);
+  return prev;
 }
 
 int b200rl_malloc(void** out_dev, uint64_t bytes) {
@@ -108,6 +128,36 @@ int b200rl_replay_append(b200rl_replay* h, int group, const float* rows_host, in
 int b200rl_replay_append_device(b200rl_replay* h, int group, const float* rows_dev, int64_t count, void* stream) {
   B200_REQUIRE(h && rows_dev, "null argument");
   return h->r.append(group, rows_dev, count, cudaMemcpyDeviceToDevice, as_stream(stream));
+}
+int b200rl_replay_set_action_norm(b200rl_replay* h, const float* scale_host, const float* bias_host) {
+  B200_REQUIRE(h && scale_host && bias_host, "null argument");
+  return h->r.set_action_norm(scale_host, bias_host);
+}
+static bool is_device_pointer(const void* p) {
+#ifndef B200_EMU
+  cudaPointerAttributes at;
+  const bool dev = cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+  (void)cudaGetLastError();
+  return dev;
+#else
+  (void)p;
+  return false;
+#endif
+}
+int b200rl_replay_append_raw(b200rl_replay* h, int group, const float* rows, int64_t count, void* stream) {
+  B200_REQUIRE(h && rows, "null argument");
+  B200_REQUIRE(count <= 64, "append_raw: at most 64 rows per call");
+  return h->r.append(group, rows, count, is_device_pointer(rows) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, as_stream(stream), true);
+}
+int b200rl_replay_append_all(b200rl_replay* h, const float* rows, int64_t count, int raw_actions, void* stream) {
+  B200_REQUIRE(h && rows, "null argument");
+  return h->r.append_all(rows, count, is_device_pointer(rows) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, as_stream(stream), raw_actions != 0);
+}
+int b200rl_replay_append_transitions(b200rl_replay* h, int group, int n, const float* obs_host, const float* action_host, const float* reward_host,
+                                     const float* next_obs_host, const float* notdone_host, int raw_actions, void* stream) {
+  B200_REQUIRE(h && obs_host && action_host && reward_host && next_obs_host && notdone_host, "null argument");
+  B200_REQUIRE(group >= 0 && group < h->r.groups, "bad group");
+  return h->r.append_transitions(group, n, obs_host, action_host, reward_host, next_obs_host, notdone_host, raw_actions != 0, as_stream(stream));
 }
 int b200rl_replay_sample(b200rl_replay* h, int batch, const float* u_dev, float* state_dev, float* action_dev, float* reward_dev, float* next_state_dev,
                          float* done_dev, void* stream) {
@@ -225,8 +275,60 @@ static int build_act_path(b200rl_agent* h) {
     B200_TRY(up(h->act_t[2], PV{fwd_problem(m.pol, 2, {h->ah2}, h->aout, m.sac ? kActNone : kActTanh)}));
     h->n_act_t = 3;
   }
+  // ---- fused path (one cluster kernel per call)
+  ActArgs& aa = h->act_args;
+  memset(&aa, 0, sizeof(aa));
+  auto layer = [](const Net& n, int l) {
+    const LayerDesc& d = n.L.layers[l];
+    ActLayer r;
+    r.W = n.p + d.w_off; r.b = n.p + d.b_off; r.gs = n.gs; r.ld = d.ld; r.in = d.in; r.out = d.out;
+    return r;
+  };
+  aa.S = S; aa.H = H; aa.Z = Z; aa.Aout = Aout;
+  aa.vmax = (int)round_up(std::max(H, std::max(Z, 4)), 4);
+  if (h->td7) {
+    TD7Agent& t = *h->td7;
+    aa.kind = 0;
+    for (int l = 0; l < 3; ++l) aa.L[l] = layer(t.fe, l);
+    for (int l = 0; l < 4; ++l) aa.L[3 + l] = layer(t.pol, l);
+  } else {
+    MlpAgent& m = *h->mlp;
+    aa.kind = m.sac ? 2 : 1;
+    for (int l = 0; l < 3; ++l) aa.L[l] = layer(m.pol, l);
+  }
+  aa.total_ctas = (unsigned)(a.G * kActCluster);
+  h->act_smem = (int)((round_up(S, 4) + 4ll * aa.vmax) * sizeof(float));
+  B200_REQUIRE(h->act_smem <= 200 * 1024, "acting path: observation / hidden sizes too large for the fused kernel");
+#ifndef B200_EMU
+  B200_TRY(a.arena.alloc(&h->d_done, 1));
+  B200_CHECK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->h_obs), (size_t)a.G * S * sizeof(float), cudaHostAllocMapped));
+  B200_CHECK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->h_act), (size_t)a.G * Aout * sizeof(float), cudaHostAllocMapped));
+  B200_CHECK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->h_tag), 64, cudaHostAllocMapped));
+  B200_CHECK_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->d_obs_map), h->h_obs, 0));
+  B200_CHECK_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->d_act_map), h->h_act, 0));
+  B200_CHECK_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->d_tag_map), h->h_tag, 0));
+  *h->h_tag = 0ull;
+  if (h->act_smem > 48 * 1024) B200_CHECK_CUDA(cudaFuncSetAttribute(act_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->act_smem));
+#endif
   return kOk;
 }
+
+#ifndef B200_EMU
+static inline bool use_fused_act() {
+  static const bool on = [] { const char* e = getenv("B200RL_ACT_FUSED"); return e ? atoi(e) != 0 : true; }();  // 0: the launch-table path
+  return on;
+}
+static int launch_act_fused(b200rl_agent* h, const float* obs, long long obs_gs, float* out, long long out_gs, bool tag, cudaStream_t s) {
+  ActArgs aa = h->act_args;
+  aa.obs = obs; aa.obs_gs = obs_gs; aa.out = out; aa.out_gs = out_gs;
+  aa.done = h->d_done;
+  aa.tag = tag ? h->d_tag_map : nullptr;
+  aa.tag_value = tag ? ++h->act_seq : 0ull;
+  B200_LAUNCH(act_fused_kernel, dim3((unsigned)(h->base->G * kActCluster)), dim3(kActThreads), (size_t)h->act_smem, s, aa);
+  B200_CHECK_LAUNCH();
+  return kOk;
+}
+#endif
 
 int b200rl_td7_create(const b200rl_td7_config* c, b200rl_agent** out) {
   B200_REQUIRE(c && out, "null argument");
@@ -305,13 +407,15 @@ int b200rl_agent_layer_info(const b200rl_agent* h, int net, int layer, int64_t* 
 
 static int net_blob(b200rl_agent* h, int net, int which, int group, float** ptr, long long* numel) {
   B200_REQUIRE(h && net >= 0 && net < b200rl_agent_net_count(h), "bad handle or net id");
-  B200_REQUIRE(group >= 0 && group < h->base->G, "bad group");
+  B200_REQUIRE(group >= -1 && group < h->base->G, "bad group");
   B200_REQUIRE(which >= 0 && which <= 3, "which must be 0..3");
+  const bool all = group < 0;  // every stacked seed: the blobs of one network are contiguous [groups][numel]
+  if (all) group = 0;
   if (is_temp_net(h, net)) {
     MlpAgent& m = *h->mlp;
     float* arr[4] = {m.la_p, m.la_m, m.la_v, m.la_g};
     *ptr = arr[which] + group;
-    *numel = 1;
+    *numel = all ? h->base->G : 1;
     return kOk;
   }
   Net* n = h->nets[net];
@@ -321,7 +425,7 @@ static int net_blob(b200rl_agent* h, int net, int which, int group, float** ptr,
     return kErrState;
   }
   *ptr = arr[which] + (long long)group * n->gs;
-  *numel = n->L.numel;
+  *numel = all ? (long long)h->base->G * n->L.numel : n->L.numel;
   return kOk;
 }
 int b200rl_agent_read(b200rl_agent* h, int net, int which, int group, float* out_host, void* stream) {
@@ -395,20 +499,23 @@ int b200rl_agent_set_counters(b200rl_agent* h, int64_t n_runs, const int64_t* ad
     st.b1pow[k] = pow(hy[k].beta1, (double)adam_steps[k]);
     st.b2pow[k] = pow(hy[k].beta2, (double)adam_steps[k]);
   }
+  st.mail = h->base->d_mail;  // the pinned loss mailbox belongs to the handle, not to the restored counters
   B200_CHECK_CUDA(cudaMemcpyAsync(h->base->d_step, &st, sizeof(st), cudaMemcpyHostToDevice, as_stream(stream)));
   B200_CHECK_CUDA(cudaStreamSynchronize(as_stream(stream)));
   h->base->n_calls = n_runs;
   return kOk;
 }
 int b200rl_td7_value_range(b200rl_agent* h, int group, float* out4_host, void* stream) {
-  B200_REQUIRE(h && h->td7 && out4_host && group >= 0 && group < h->base->G, "not a TD7 agent / bad group");
-  B200_CHECK_CUDA(cudaMemcpyAsync(out4_host, h->td7->d_range + group, sizeof(TD7Range), cudaMemcpyDeviceToHost, as_stream(stream)));
+  B200_REQUIRE(h && h->td7 && out4_host && group >= -1 && group < h->base->G, "not a TD7 agent / bad group");
+  B200_CHECK_CUDA(cudaMemcpyAsync(out4_host, h->td7->d_range + (group < 0 ? 0 : group), (group < 0 ? h->base->G : 1) * sizeof(TD7Range), cudaMemcpyDeviceToHost,
+                                  as_stream(stream)));
   B200_CHECK_CUDA(cudaStreamSynchronize(as_stream(stream)));
   return kOk;
 }
 int b200rl_td7_set_value_range(b200rl_agent* h, int group, const float* in4_host, void* stream) {
-  B200_REQUIRE(h && h->td7 && in4_host && group >= 0 && group < h->base->G, "not a TD7 agent / bad group");
-  B200_CHECK_CUDA(cudaMemcpyAsync(h->td7->d_range + group, in4_host, sizeof(TD7Range), cudaMemcpyHostToDevice, as_stream(stream)));
+  B200_REQUIRE(h && h->td7 && in4_host && group >= -1 && group < h->base->G, "not a TD7 agent / bad group");
+  B200_CHECK_CUDA(cudaMemcpyAsync(h->td7->d_range + (group < 0 ? 0 : group), in4_host, (group < 0 ? h->base->G : 1) * sizeof(TD7Range), cudaMemcpyHostToDevice,
+                                  as_stream(stream)));
   B200_CHECK_CUDA(cudaStreamSynchronize(as_stream(stream)));
   return kOk;
 }
@@ -471,16 +578,18 @@ int b200rl_agent_info_cols(const b200rl_agent* h) { return h ? h->base->info_col
 int b200rl_agent_read_info(b200rl_agent* h, int64_t first_step, int count, int group, float* out_host, void* stream) {
   B200_REQUIRE(h && out_host, "null argument");
   AgentBase& a = *h->base;
-  B200_REQUIRE(group >= 0 && group < a.G, "bad group");
+  B200_REQUIRE(group >= -1 && group < a.G, "bad group");
   B200_REQUIRE(count >= 0 && count <= kInfoRing, "at most 1024 steps stay readable");
   B200_REQUIRE(first_step >= 1 && first_step + count - 1 <= a.n_calls && first_step > a.n_calls - kInfoRing, "step range is not (or no longer) in the info ring");
   cudaStream_t s = as_stream(stream);
-  const float* ring = a.d_info + (long long)group * kInfoRing * a.info_cols;
+  // group = -1: every stacked seed, out_host [groups][count][cols] -- one strided copy per contiguous run of the ring
+  const int ngroups = group < 0 ? a.G : 1;
+  const float* ring = a.d_info + (long long)(group < 0 ? 0 : group) * kInfoRing * a.info_cols;
   for (int i = 0; i < count;) {
     const int slot = (int)((first_step - 1 + i) % kInfoRing);
     const int run = std::min(count - i, kInfoRing - slot);
-    B200_CHECK_CUDA(cudaMemcpyAsync(out_host + (long long)i * a.info_cols, ring + (long long)slot * a.info_cols, (size_t)run * a.info_cols * sizeof(float),
-                                    cudaMemcpyDeviceToHost, s));
+    B200_CHECK_CUDA(cudaMemcpy2DAsync(out_host + (long long)i * a.info_cols, (size_t)count * a.info_cols * sizeof(float), ring + (long long)slot * a.info_cols,
+                                      (size_t)kInfoRing * a.info_cols * sizeof(float), (size_t)run * a.info_cols * sizeof(float), (size_t)ngroups, cudaMemcpyDeviceToHost, s));
     i += run;
   }
   B200_CHECK_CUDA(cudaStreamSynchronize(s));
@@ -513,6 +622,9 @@ int b200rl_agent_act(b200rl_agent* h, const float* obs_dev, float* out_dev, void
   AgentBase& a = *h->base;
   cudaStream_t s = as_stream(stream);
   const int G = a.G;
+#ifndef B200_EMU
+  if (use_fused_act()) return launch_act_fused(h, obs_dev, a.S, out_dev, h->aout.cols, false, s);
+#endif
   for (int g = 0; g < G; ++g)
     B200_CHECK_CUDA(cudaMemcpyAsync(h->o_s.p + (long long)g * h->o_s.gs, obs_dev + (long long)g * a.S, (size_t)a.S * sizeof(float), cudaMemcpyDeviceToDevice, s));
   if (h->td7) {
@@ -532,6 +644,47 @@ int b200rl_agent_act(b200rl_agent* h, const float* obs_dev, float* out_dev, void
   return kOk;
 }
 
+int b200rl_agent_act_host(b200rl_agent* h, const float* obs_host, float* out_host, void* stream) {
+  B200_REQUIRE(h && obs_host && out_host, "null argument");
+  AgentBase& a = *h->base;
+  cudaStream_t s = as_stream(stream);
+  const int G = a.G, Aout = h->aout.cols;
+#ifndef B200_EMU
+  if (use_fused_act()) {
+    memcpy(h->h_obs, obs_host, (size_t)G * a.S * sizeof(float));
+    B200_TRY(launch_act_fused(h, h->d_obs_map, a.S, h->d_act_map, Aout, true, s));
+    const volatile unsigned long long* tag = h->h_tag;
+    const unsigned long long want = h->act_seq;
+    const auto t0 = std::chrono::steady_clock::now();
+    long spins = 0;
+    while (*tag != want) {
+      if ((++spins & 0xfff) == 0) {
+        if (cudaStreamQuery(s) == cudaSuccess && *tag != want) { (void)cudaGetLastError(); break; }  // ran without posting: fall through to the check
+        (void)cudaGetLastError();
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(10)) { set_last_error("agent_act_host: the acting kernel did not post its result"); return kErrCuda; }
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    if (*tag != want) { B200_CHECK_CUDA(cudaStreamSynchronize(s)); if (*tag != want) { set_last_error("agent_act_host: acting kernel failed"); return kErrCuda; } }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    memcpy(out_host, h->h_act, (size_t)G * Aout * sizeof(float));
+    return kOk;
+  }
+#endif
+  // launch-table path: stage through device buffers
+  DeviceArena tmp;
+  float *o = nullptr, *y = nullptr;
+  B200_TRY(tmp.alloc(&o, (size_t)G * a.S));
+  B200_TRY(tmp.alloc(&y, (size_t)G * Aout));
+  B200_CHECK_CUDA(cudaMemcpyAsync(o, obs_host, (size_t)G * a.S * sizeof(float), cudaMemcpyHostToDevice, s));
+  B200_TRY(b200rl_agent_act(h, o, y, stream));
+  B200_CHECK_CUDA(cudaMemcpyAsync(out_host, y, (size_t)G * Aout * sizeof(float), cudaMemcpyDeviceToHost, s));
+  B200_CHECK_CUDA(cudaStreamSynchronize(s));
+  return kOk;
+}
+
 int b200rl_agent_debug_read(b200rl_agent* h, int which, int group, float* out_host, void* stream) {
   B200_REQUIRE(h && out_host, "null argument");
   AgentBase& a = *h->base;
@@ -539,13 +692,13 @@ int b200rl_agent_debug_read(b200rl_agent* h, int which, int group, float* out_ho
   const Mat* m = nullptr;
   if (h->td7) {
     TD7Agent& t = *h->td7;
-    const Mat* tab[5] = {&t.y_dbg, &t.prio_dbg, &t.qv[0], &t.qv[1], &t.a_pi};
-    B200_REQUIRE(which >= 0 && which < 5, "which must be 0..4");
+    const Mat* tab[6] = {&t.y_dbg, &t.prio_dbg, &t.qv[0], &t.qv[1], &t.a_pi, &t.noise};
+    B200_REQUIRE(which >= 0 && which < 6, "which must be 0..5");
     m = tab[which];
   } else {
     MlpAgent& t = *h->mlp;
-    const Mat* tab[5] = {&t.y_dbg, &t.prio_dbg, &t.qv[0], &t.qv[1], &t.a_pi};
-    B200_REQUIRE(which >= 0 && which < 5, "which must be 0..4");
+    const Mat* tab[7] = {&t.y_dbg, &t.prio_dbg, &t.qv[0], &t.qv[1], &t.a_pi, &t.noise, &t.noise2};
+    B200_REQUIRE(which >= 0 && which < (t.sac ? 7 : 6), "which must be 0..5 (SAC: 0..6)");
     m = tab[which];
   }
   B200_CHECK_CUDA(cudaMemcpyAsync(out_host, m->p + (long long)group * m->gs, (size_t)m->rows * m->cols * sizeof(float), cudaMemcpyDeviceToHost, as_stream(stream)));

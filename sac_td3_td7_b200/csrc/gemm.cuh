@@ -197,16 +197,30 @@ __device__ __forceinline__ void cp_async_wait() {
 #endif
 }
 
+// Shared-memory swizzles.  Both tile layouts are XOR-swizzled at float4 (16-byte) granularity so that the cp.async
+// writes stay 16-byte contiguous and the reads of the math loop are bank-conflict free:
+//   FFMA loop: K-major slot ^= (row >> 2) & 7 (strided per-lane float4 reads); C-major rows are read as they are.
+//   MMA loop (mma.sync fragments, scalar reads of lane (g = lane >> 2, t = lane & 3)): K-major slot ^= row & 7 (eight
+//   consecutive rows x four t's hit 32 different banks); C-major slot ^= (r & 3) << 1 (four consecutive reduction
+//   rows x eight consecutive output indices hit 32 different banks).
+template <bool MMA>
+__device__ __forceinline__ int km_swz(int row) { return MMA ? (row & 7) : ((row >> 2) & 7); }
+template <bool MMA>
+__device__ __forceinline__ int cm_swz(int r) { return MMA ? ((r & 3) << 1) : 0; }
+// K-major: float offset of the strip 16 rows below `dst` (same 16-byte slot of the unswizzled row)
+template <bool MMA>
+__device__ __forceinline__ int km_second_strip(int dst) { return MMA ? dst + 16 * kBK : (dst ^ 16) + 16 * kBK; }
+
 // copy one thread's two strips of the chunk starting at reduction offset r0 (segment length rlen), zero-filling
 // whatever lies outside the operand
-template <bool KMAJOR>
+template <bool KMAJOR, bool MMA>
 B200_NOINLINE __device__ void stage_ragged(float* tile, const float* src, int delta, int dst, int pos, int row, bool ok0, bool ok1, bool vec, int r0, int rlen,
                                            int cmax) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const float* q = src + (h ? delta : 0);
     if (KMAJOR) {
-      float* d = tile + (h ? ((dst ^ 16) + 16 * kBK) : dst);
+      float* d = tile + (h ? (km_second_strip<MMA>(dst)) : dst);
       const int p = r0 + pos;
       const bool ok = h ? ok1 : ok0;
       if (vec && ok && p + 3 < rlen) {
@@ -249,7 +263,7 @@ B200_NOINLINE __device__ void stage_ragged(float* tile, const float* src, int de
 // shared-memory offset) is computed once per segment; per chunk the fast path is one bounds test,
 // one cp.async per strip and one pointer bump.  The second strip sits 16 rows (K-major) / 32 rows
 // (C-major) below the first, so one pointer, one stride and one offset describe both.
-template <bool KMAJOR>
+template <bool KMAJOR, bool MMA>
 struct OperandCursor {
   const float* src;  // strip 0 of the next chunk; strip 1 = src + delta
   int delta;         // K-major: 16 * ld; C-major: 32 * ld
@@ -263,7 +277,7 @@ struct OperandCursor {
   __device__ __forceinline__ void init(const float* base, int ld, int c0, int cmax, int tid, int r_start) {
     if (KMAJOR) {
       const int c = tid >> 4, s = tid & 15;
-      dst = c * kBK + ((s ^ ((c >> 2) & 7)) << 2);
+      dst = c * kBK + ((s ^ km_swz<MMA>(c)) << 2);
       pos = s << 2;
       row = 0;
       ok0 = (c0 + c) < cmax;
@@ -274,7 +288,7 @@ struct OperandCursor {
       all = vec && ok0 && ok1;
     } else {
       const int r = tid >> 3, s = tid & 7;
-      dst = r * kTile + (s << 2);
+      dst = r * kTile + ((s ^ cm_swz<MMA>(r)) << 2);
       pos = c0 + (s << 2);
       row = r;
       ok0 = ok1 = pos < cmax;
@@ -288,7 +302,7 @@ struct OperandCursor {
   __device__ __forceinline__ void stage_full(float* tile) {
     if (KMAJOR) {
       cp_async16(tile + dst, src);
-      cp_async16(tile + ((dst ^ 16) + 16 * kBK), src + delta);
+      cp_async16(tile + km_second_strip<MMA>(dst), src + delta);
       src += kBK;
     } else {
       cp_async16(tile + dst, src);
@@ -298,18 +312,19 @@ struct OperandCursor {
   }
   // general path (ragged widths such as 17 / 6 / 23, segment tails, unaligned rows): out of line, it is rare
   __device__ __forceinline__ void stage(float* tile, int r0, int rlen, int cmax) {
-    stage_ragged<KMAJOR>(tile, src, delta, dst, pos, row, ok0, ok1, vec, r0, rlen, cmax);
+    stage_ragged<KMAJOR, MMA>(tile, src, delta, dst, pos, row, ok0, ok1, vec, r0, rlen, cmax);
     src += KMAJOR ? (long long)kBK : 2ll * delta;
   }
 };
 
 // bias-gradient problems: B(r, j) = (j == 0)   (C-major tile)
+template <bool MMA>
 __device__ __forceinline__ void stage_ones(float* tile, int c0, int r0, int rlen, int tid) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int r = (tid >> 3) + 32 * h, s = tid & 7;
     const float one = ((r0 + r) < rlen && s == 0 && c0 == 0) ? 1.f : 0.f;
-    *reinterpret_cast<float4*>(tile + r * kTile + (s << 2)) = make_float4(one, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(tile + r * kTile + ((s ^ cm_swz<MMA>(r)) << 2)) = make_float4(one, 0.f, 0.f, 0.f);
   }
 }
 
@@ -399,6 +414,26 @@ __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b)
 #endif
 }
 
+// ---- error-compensated TF32 on the warp-level tensor-core path (3xTF32) -------------------------------------------
+// x = hi + lo with hi = tf32(x) and lo = tf32(x - hi) (both round-to-nearest): hi carries 11 significant bits, lo the next
+// 11, so a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi is short of the exact fp32 product by ~2^-22 relative (the dropped
+// a_lo*b_lo term) -- below the rounding of an fp32 FFMA chain.  The products are accumulated in fp32 by
+// mma.sync.m16n8k8 (small terms first).  Not available to the host emulation, which keeps the FFMA loop.
+#ifndef B200_EMU
+__device__ __forceinline__ void tf32_split(float x, unsigned& hi, unsigned& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+// D(16x8) += A(16x8, row) * B(8x8, col); lane (g = lane >> 2, t = lane & 3) holds a0 = A[g][t], a1 = A[g+8][t],
+// a2 = A[g][t+4], a3 = A[g+8][t+4]; b0 = B[t][g], b1 = B[t+4][g]; d0 = D[g][2t], d1 = D[g][2t+1], d2 = D[g+8][2t], d3 = D[g+8][2t+1]
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+#endif
+
 // four consecutive floats of an epilogue operand, all loads in flight at once
 __device__ __forceinline__ void load_quad(float (&o)[4], const float* p, int nvalid) {
   if (nvalid == 4 && aligned16(p)) {
@@ -422,7 +457,10 @@ __device__ __forceinline__ void store_quad(float* p, const float (&o)[4], int nv
 // Register budget: two CTAs per SM (<= 128 registers).  A variant without the cap was measured (fewer address
 // recomputations in the loop) and lost: a single agent's update keeps several small launches of different streams in
 // flight, and they only overlap if two CTAs fit on one SM.
-template <int MODE>
+// MMA = true: the chunk products run on the tensor cores as 3xTF32 (mma.sync fragments read straight from the same
+// cp.async-staged tiles, with the fragment-friendly swizzles); everything around the product loop -- staging, split-K
+// clusters, the fixed-order cross-warp reduction, the fused epilogues -- is shared with the FFMA variant.
+template <int MODE, bool MMA>
 __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_constant__ FfmaLaunch L) {
   B200_PDL_TRIGGER();  // the setup below reads kernel parameters only: it may overlap the previous kernel
   B200_PROBE_DECL
@@ -479,8 +517,8 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_cons
   const int nchunks = max(0, min(sp.per_split, sp.total_chunks - c_begin));
 
   // producer cursor
-  OperandCursor<A_KM> ca;
-  OperandCursor<B_KM> cb;
+  OperandCursor<A_KM, MMA> ca;
+  OperandCursor<B_KM, MMA> cb;
   int pseg = 0, pr0 = 0, plen = 0;
   bool ones = false;
   auto open_segment = [&](int r_start) {
@@ -497,7 +535,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_cons
     const bool full = pr0 + kBK <= plen;
     if (full && ca.all) ca.stage_full(At);
     else ca.stage(At, pr0, plen, I);
-    if (ones) stage_ones(Bt, j0, pr0, plen, tid);
+    if (ones) stage_ones<MMA>(Bt, j0, pr0, plen, tid);
     else if (full && cb.all) cb.stage_full(Bt);
     else cb.stage(Bt, pr0, plen, J);
     pr0 += kBK;
@@ -544,6 +582,29 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_cons
     for (int b = 0; b < 8; ++b) b_off[b] = (warp * 8 + (b >> 1)) * kTile + lj * 8 + 4 * (b & 1);  // rr = b >> 1, half-row b & 1
   }
 
+  // MMA fragments: lane (fg = lane >> 2, ft = lane & 3); the warp's k8 step is r = 8*warp + {ft, ft + 4}
+  int ma_off[2][4], mb_off[4][2];
+  float macc[2][4][4];
+  {
+    const int fg = lane >> 2, ft = lane & 3;
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = 16 * mi + fg + 8 * (q & 1), r = 8 * warp + ft + 4 * (q >> 1);
+        ma_off[mi][q] = A_KM ? i * kBK + ((((r >> 2) ^ km_swz<true>(i)) << 2) | (r & 3)) : r * kTile + ((((i >> 2) ^ cm_swz<true>(r)) << 2) | (i & 3));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) macc[mi][q][e] = 0.f;  // (q doubles as the n index here: 2 x 4 x 4 accumulators)
+      }
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int n = 8 * ni + fg, r = 8 * warp + ft + 4 * q;
+        mb_off[ni][q] = B_KM ? n * kBK + ((((r >> 2) ^ km_swz<true>(n)) << 2) | (r & 3)) : r * kTile + ((((n >> 2) ^ cm_swz<true>(r)) << 2) | (n & 3));
+      }
+  }
+
   int rs = 0, ws = kStages - 1;  // stage read by chunk c / stage refilled during chunk c
   for (int c = 0; c < nchunks; ++c) {
     cp_async_wait<kStages - 2>();  // chunk c has landed (this thread's copies)
@@ -556,7 +617,29 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_cons
     const float* Bs = As + kTile * kBK;
     rs = (rs + 1 == kStages) ? 0 : rs + 1;
     ws = (ws + 1 == kStages) ? 0 : ws + 1;
-    // this warp's 8 reduction indices of the chunk: r = 8*warp .. 8*warp+7, in two halves of 4
+    // this warp's 8 reduction indices of the chunk: r = 8*warp .. 8*warp+7
+#ifndef B200_EMU
+    if (MMA) {
+      // one k8 step of the whole 32 x 32 tile: 2 (m16) x 4 (n8) fragments, each product as three TF32 MMAs
+      unsigned ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tf32_split(As[ma_off[mi][q]], ah[mi][q], al[mi][q]);
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) tf32_split(Bs[mb_off[ni][q]], bh[ni][q], bl[ni][q]);
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          mma_tf32(macc[mi][ni], al[mi], bh[ni]);
+          mma_tf32(macc[mi][ni], ah[mi], bl[ni]);
+          mma_tf32(macc[mi][ni], ah[mi], bh[ni]);
+        }
+    } else
+#endif
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       float av[4][4], bv[8][4];  // [output index][r within the half]
@@ -653,17 +736,31 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_cons
 #pragma unroll
       for (int b = 0; b < 8; ++b) acc[a][b] = (b & 1) ? acc2[a][b >> 1].y : acc2[a][b >> 1].x;
   }
+  if (MMA) {
+    const int fg = lane >> 2, ft = lane & 3;
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int row = li * 4 + a;
-    float* base = part + warp * kTileElems + row * kTile;
-    *reinterpret_cast<float4*>(base + (((2 * lj) ^ li) << 2)) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
-    *reinterpret_cast<float4*>(base + (((2 * lj + 1) ^ li) << 2)) = make_float4(acc[a][4], acc[a][5], acc[a][6], acc[a][7]);
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int row = 16 * mi + fg + 8 * hh, col = 8 * ni + 2 * ft;
+          float* base = part + warp * kTileElems + row * kTile;
+          *reinterpret_cast<float2*>(base + ((((col >> 2) ^ km_swz<true>(row)) << 2) | (col & 3))) = make_float2(macc[mi][ni][2 * hh], macc[mi][ni][2 * hh + 1]);
+        }
+  } else {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int row = li * 4 + a;
+      float* base = part + warp * kTileElems + row * kTile;
+      *reinterpret_cast<float4*>(base + (((2 * lj) ^ li) << 2)) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+      *reinterpret_cast<float4*>(base + (((2 * lj + 1) ^ li) << 2)) = make_float4(acc[a][4], acc[a][5], acc[a][6], acc[a][7]);
+    }
   }
   __syncthreads();
   float out[4];
   {
-    const float* p0 = part + oi * kTile + ((oslot ^ ((oi >> 2) & 7)) << 2);
+    const float* p0 = part + oi * kTile + ((oslot ^ km_swz<MMA>(oi)) << 2);
     float4 s = *reinterpret_cast<const float4*>(p0);
 #pragma unroll
     for (int w = 1; w < 8; ++w) {

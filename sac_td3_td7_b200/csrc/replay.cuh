@@ -395,26 +395,51 @@ __global__ void lap_append_priority_kernel(float* __restrict__ priority, const f
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) priority[(pos + i) % cap] = *max_priority;
 }
-// the per-environment-step form (a handful of rows): one CTA copies the rows -- `src` may be device memory or pinned
-// host memory read over the bus, so the step needs no separate H2D copy -- writes the priorities and repairs the sum
-// tree.  src == null: rows were copied by the caller; priority == null: uniform buffer.
-__global__ void __launch_bounds__(1024) lap_append_fix_kernel(const float* __restrict__ src, float* __restrict__ dst_base, int row_stride,
-                                                              float* __restrict__ priority, const float* __restrict__ max_priority, FixArgs fix) {
+// the per-environment-step form (a handful of rows per stacked seed): one CTA per seed copies that seed's rows -- `src`
+// may be device memory or pinned host memory read over the bus, so the step needs no separate H2D copy --, applies the
+// reference's action normalisation a/scale - bias (lap.py:35; IEEE fp32 division and subtraction, i.e. exactly numpy's
+// result for the fp32 actions the agents emit) when asked to, writes the priorities and repairs the sum tree.
+// src == null: rows were copied by the caller; priority == null: uniform buffer; dst_gs == 0: one shared row store
+// (only the first seed's CTA copies).
+struct AppendArgs {
+  const float* src; long long src_gs;
+  float* dst; long long dst_gs;
+  int row_stride, group0;
+  float* priority; long long prio_gs;
+  const float* max_priority;
+  const float* act_scale; const float* act_bias;
+  int S, A;
+  FixArgs fix;  // base pointers of group 0, per-group strides inside
+};
+__global__ void __launch_bounds__(1024) lap_append_fix_kernel(AppendArgs a) {
   B200_PDL_PROLOGUE();
-  if (src) {
-    const int q4 = row_stride >> 2;  // float4 per row
+  const int g = a.group0 + (int)blockIdx.x;
+  const FixArgs& fix = a.fix;
+  if (a.src && (a.dst_gs != 0 || blockIdx.x == 0)) {
+    const float* src = a.src + (long long)blockIdx.x * a.src_gs;
+    float* dst_base = a.dst + (long long)g * a.dst_gs;
+    const int q4 = a.row_stride >> 2;  // float4 per row
     for (int i = threadIdx.x; i < fix.n * q4; i += blockDim.x) {
       const int r = i / q4, c = i - r * q4;
-      const float4 v = *reinterpret_cast<const float4*>(src + (long long)r * row_stride + c * 4);
-      *reinterpret_cast<float4*>(dst_base + ((fix.pos + r) % fix.cap) * row_stride + c * 4) = v;
+      const float4 v = *reinterpret_cast<const float4*>(src + (long long)r * a.row_stride + c * 4);
+      *reinterpret_cast<float4*>(dst_base + ((fix.pos + r) % fix.cap) * a.row_stride + c * 4) = v;
+    }
+    if (a.act_scale) {
+      __syncthreads();  // the action columns were just written by other threads of this block
+      for (int i = threadIdx.x; i < fix.n * a.A; i += blockDim.x) {
+        const int r = i / a.A, j = i - r * a.A;
+        float* p = dst_base + ((fix.pos + r) % fix.cap) * a.row_stride + a.S + j;
+        *p = __fsub_rn(__fdiv_rn(*p, a.act_scale[j]), a.act_bias[j]);
+      }
     }
   }
-  if (!priority) return;
-  const float m = *max_priority;
+  if (!a.priority) return;
+  float* priority = a.priority + (long long)g * a.prio_gs;
+  const float m = a.max_priority[g];
   for (int i = threadIdx.x; i < fix.n; i += blockDim.x) priority[(fix.pos + i) % fix.cap] = m;
   __threadfence_block();
   __syncthreads();
-  lap_fix_block(fix, 0);
+  lap_fix_block(fix, g);
 }
 
 // ----------------------------------------------------------------------------- host object
@@ -442,6 +467,85 @@ struct Replay {
 
   long long rows_gs() const { return share_rows ? 0 : capacity * (long long)row_stride; }
 
+  // pinned staging ring for per-step appends (rl/rollout.py:45): the append kernel reads a slot over the bus when it runs, an
+  // event per slot tells when it may be rewritten
+  static constexpr int kStageSlots = 16;
+  float* h_stage = nullptr;
+  cudaEvent_t stage_ev[kStageSlots] = {};
+  bool stage_busy[kStageSlots] = {};
+  int stage_next = 0;
+  long long stage_rows() const { return share_rows ? 1 : groups; }
+  ~Replay() {
+#ifndef B200_EMU
+    if (h_stage) {
+      cudaFreeHost(h_stage);
+      for (auto& e : stage_ev) cudaEventDestroy(e);
+    }
+#else
+    if (h_stage) free(h_stage);
+#endif
+  }
+  int stage_slot(float** out) {
+    if (!h_stage) {
+      const size_t bytes = (size_t)kStageSlots * stage_rows() * row_stride * sizeof(float);
+#ifndef B200_EMU
+      B200_CHECK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_stage), bytes, cudaHostAllocMapped));
+      for (auto& e : stage_ev) B200_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+#else
+      h_stage = static_cast<float*>(aligned_alloc(64, (bytes + 63) / 64 * 64));
+#endif
+      memset(h_stage, 0, bytes);
+    }
+    const int sl = stage_next;
+#ifndef B200_EMU
+    if (stage_busy[sl]) B200_CHECK_CUDA(cudaEventSynchronize(stage_ev[sl]));  // (16 appends ago: practically never waits)
+#endif
+    *out = h_stage + (long long)sl * stage_rows() * row_stride;
+    return kOk;
+  }
+  int stage_commit(cudaStream_t stream) {
+#ifndef B200_EMU
+    B200_CHECK_CUDA(cudaEventRecord(stage_ev[stage_next], stream));
+#else
+    (void)stream;
+#endif
+    stage_busy[stage_next] = true;
+    stage_next = (stage_next + 1) % kStageSlots;
+    return kOk;
+  }
+  // rl/rollout.py:45 + lap.py:31-43 for one environment step: `n` = 1 (one agent / one stacked seed `g`) or `groups`
+  // (every stacked seed; a shared row store takes the transition of seed 0) transitions given as separate host arrays
+  int append_transitions(int g, int n, const float* obs, const float* action, const float* reward, const float* next_obs, const float* notdone, bool raw_action,
+                         cudaStream_t stream) {
+    B200_REQUIRE(n == 1 || n == groups, "append_transitions: one transition, or one per stacked seed");
+    float* slot = nullptr;
+    B200_TRY(stage_slot(&slot));
+    const int nrows = (n == 1 || share_rows) ? 1 : groups;
+    for (int r = 0; r < nrows; ++r) {
+      float* row = slot + (long long)r * row_stride;
+      memcpy(row, obs + (long long)r * S, S * sizeof(float));
+      memcpy(row + S, action + (long long)r * A, A * sizeof(float));
+      row[S + A] = reward[r];
+      row[S + A + 1] = notdone[r];
+      memcpy(row + S + A + 2, next_obs + (long long)r * S, S * sizeof(float));
+    }
+    int st;
+    if (n == 1 && groups > 1) st = append(g, slot, 1, cudaMemcpyHostToDevice, stream, raw_action);
+    else if (groups == 1) st = append(0, slot, 1, cudaMemcpyHostToDevice, stream, raw_action);
+    else st = append_all(slot, 1, cudaMemcpyHostToDevice, stream, raw_action);
+    if (st != kOk) return st;
+    return stage_commit(stream);
+  }
+
+  float* d_act_scale = nullptr;  // action normalisation applied by append when requested (lap.py:35)
+  float* d_act_bias = nullptr;
+  int set_action_norm(const float* scale_host, const float* bias_host) {
+    if (!d_act_scale) { B200_TRY(arena.alloc(&d_act_scale, (size_t)A)); B200_TRY(arena.alloc(&d_act_bias, (size_t)A)); }
+    B200_CHECK_CUDA(cudaMemcpy(d_act_scale, scale_host, A * sizeof(float), cudaMemcpyHostToDevice));
+    B200_CHECK_CUDA(cudaMemcpy(d_act_bias, bias_host, A * sizeof(float), cudaMemcpyHostToDevice));
+    return kOk;
+  }
+
   int init(long long cap, int s, int a, int g, bool prio, bool share) {
     B200_REQUIRE(cap > 0 && s > 0 && a > 0 && g > 0, "replay: capacity, dims and groups must be positive");
     B200_REQUIRE(cap < (1LL << 31) - 4096, "replay: capacity must fit in int32");
@@ -468,28 +572,40 @@ struct Replay {
     return kOk;
   }
 
-  // rows: host or device pointer to `count` packed rows (row_stride floats each, already normalised)
-  int append(int g, const float* rows, long long count, cudaMemcpyKind kind, cudaStream_t stream) {
+  // if the GPU can read `rows` directly (device memory, or pinned / registered host memory): the pointer to use in a kernel
+  static const float* device_readable(const float* rows, cudaMemcpyKind kind) {
+#ifndef B200_EMU
+    if ((reinterpret_cast<uintptr_t>(rows) & 15) != 0) return nullptr;
+    if (kind == cudaMemcpyDeviceToDevice) return rows;
+    cudaPointerAttributes at;
+    const float* direct = nullptr;
+    if (cudaPointerGetAttributes(&at, rows) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) direct = static_cast<const float*>(at.devicePointer);
+    (void)cudaGetLastError();
+    return direct;
+#else
+    (void)kind;
+    return rows;
+#endif
+  }
+
+  // rows: host or device pointer to `count` packed rows (row_stride floats each); normalise: apply a/scale - bias to the
+  // action columns on the way in (needs set_action_norm)
+  int append(int g, const float* rows, long long count, cudaMemcpyKind kind, cudaStream_t stream, bool normalise = false) {
     B200_REQUIRE(g >= 0 && g < groups, "replay.append: bad group");
     B200_REQUIRE(count >= 0 && count <= capacity, "replay.append: count must be within capacity");
+    B200_REQUIRE(!normalise || d_act_scale, "replay.append: action normalisation requested before set_action_norm");
     if (count == 0) return kOk;
     const long long pos = ptr[g];
     const bool want_rows = !(share_rows && g > 0);
     float* dst_base = d_rows + (share_rows ? 0 : (long long)g * capacity * row_stride);
     // small appends (the per-step case) whose source the GPU can read directly -- device memory, or pinned / registered
-    // host memory -- are ONE kernel: row copy + priorities + tree repair
+    // host memory -- are ONE kernel: row copy (+ action normalisation) + priorities + tree repair
     const float* direct = nullptr;
-#ifndef B200_EMU
-    if (want_rows && count <= 64 && (reinterpret_cast<uintptr_t>(rows) & 15) == 0 && (!prioritized || sums_valid)) {
-      if (kind == cudaMemcpyDeviceToDevice) {
-        direct = rows;
-      } else {
-        cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, rows) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) direct = static_cast<const float*>(at.devicePointer);
-        (void)cudaGetLastError();
-      }
-    }
+    if (want_rows && count <= 64 && (!prioritized || sums_valid)) direct = device_readable(rows, kind);
+#ifdef B200_EMU
+    if (!normalise) direct = nullptr;  // (the emulation keeps the memcpy path it always had, except where the kernel must transform)
 #endif
+    B200_REQUIRE(!normalise || direct || !want_rows, "replay.append: device-side normalisation needs <= 64 rows the GPU can read (pinned host or device memory)");
     if (want_rows && !direct) {
       const long long first = std::min(count, capacity - pos);
       B200_CHECK_CUDA(cudaMemcpyAsync(dst_base + pos * row_stride, rows, (size_t)first * row_stride * sizeof(float), kind, stream));
@@ -498,16 +614,19 @@ struct Replay {
     }
     if (prioritized || direct) {
       if (count <= 4096 && (sums_valid || !prioritized)) {
-        FixArgs f;
-        memset(&f, 0, sizeof(f));
-        if (prioritized) {
-          f = fix_args(nullptr, 0, (int)count);
-          f.priority += (long long)g * cap_pad; f.tile_sums += (long long)g * max_tiles; f.super_sums += (long long)g * max_supers;
-        }
-        f.n = (int)count; f.cap = capacity;
-        f.pos = pos;
-        B200_LAUNCH(lap_append_fix_kernel, dim3(1), dim3(count <= 32 ? 64 : 1024), 0, stream, direct, dst_base, row_stride,
-                    prioritized ? d_priority + (long long)g * cap_pad : nullptr, d_max_priority + g, f);
+        AppendArgs a;
+        memset(&a, 0, sizeof(a));
+        if (prioritized) a.fix = fix_args(nullptr, 0, (int)count);
+        a.fix.n = (int)count; a.fix.cap = capacity; a.fix.pos = pos;
+        a.src = direct; a.src_gs = 0;
+        a.dst = d_rows; a.dst_gs = share_rows ? 0 : capacity * (long long)row_stride;
+        a.row_stride = row_stride; a.group0 = g;
+        a.priority = prioritized ? d_priority : nullptr; a.prio_gs = cap_pad;
+        a.max_priority = d_max_priority;
+        if (normalise) { a.act_scale = d_act_scale; a.act_bias = d_act_bias; }
+        a.S = S; a.A = A;
+        if (share_rows && g > 0) a.src = nullptr;
+        B200_LAUNCH(lap_append_fix_kernel, dim3(1), dim3(count <= 32 ? 64 : 1024), 0, stream, a);
       } else {
         dim3 grid((unsigned)ceil_div((int)count, 256)), block(256);
         B200_LAUNCH(lap_append_priority_kernel, grid, block, 0, stream, d_priority + (long long)g * cap_pad, d_max_priority + g, pos, (int)count, capacity);
@@ -517,6 +636,39 @@ struct Replay {
     }
     ptr[g] = (pos + count) % capacity;
     size[g] = std::min(size[g] + count, capacity);
+    return kOk;
+  }
+
+  // one environment step of a whole population: `count` (<= 64) rows for EVERY stacked seed in one launch.  rows:
+  // [groups][count][row_stride] (private row stores) or [count][row_stride] (shared row store), readable by the GPU.
+  int append_all(const float* rows, long long count, cudaMemcpyKind kind, cudaStream_t stream, bool normalise) {
+    B200_REQUIRE(count > 0 && count <= 64, "replay.append_all: 1..64 rows per seed");
+    B200_REQUIRE(!normalise || d_act_scale, "replay.append_all: action normalisation requested before set_action_norm");
+    for (int g = 1; g < groups; ++g) B200_REQUIRE(ptr[g] == ptr[0] && size[g] == size[0], "replay.append_all: stacked seeds must share one cursor");
+    if (prioritized && !sums_valid) {
+      long long n;
+      B200_TRY(common_size(&n));
+      B200_TRY(rebuild_sums(n, stream));
+    }
+    const float* direct = device_readable(rows, kind);
+    B200_REQUIRE(direct != nullptr, "replay.append_all: rows must be device memory or pinned host memory, 16-byte aligned");
+    AppendArgs a;
+    memset(&a, 0, sizeof(a));
+    if (prioritized) a.fix = fix_args(nullptr, 0, (int)count);
+    a.fix.n = (int)count; a.fix.cap = capacity; a.fix.pos = ptr[0];
+    a.src = direct; a.src_gs = share_rows ? 0 : count * (long long)row_stride;
+    a.dst = d_rows; a.dst_gs = share_rows ? 0 : capacity * (long long)row_stride;
+    a.row_stride = row_stride; a.group0 = 0;
+    a.priority = prioritized ? d_priority : nullptr; a.prio_gs = cap_pad;
+    a.max_priority = d_max_priority;
+    if (normalise) { a.act_scale = d_act_scale; a.act_bias = d_act_bias; }
+    a.S = S; a.A = A;
+    B200_LAUNCH(lap_append_fix_kernel, dim3((unsigned)groups), dim3(count <= 32 ? 64 : 1024), 0, stream, a);
+    B200_CHECK_LAUNCH();
+    for (int g = 0; g < groups; ++g) {
+      ptr[g] = (ptr[g] + count) % capacity;
+      size[g] = std::min(size[g] + count, capacity);
+    }
     return kOk;
   }
 

@@ -66,5 +66,34 @@ class Population:
     def train(self, n_updates: int):
         return self.agent.train_ops_n(n_updates, self.replay)
 
+    def evaluate(self, envs, n_episodes: int = 10, deterministic: bool = True):
+        """``test_agent`` (rl/runner/run.py:21-45) for every stacked seed of this rank at once: seed g acts in
+        ``envs[g]`` (gymnasium API: ``reset() -> (obs, info)``, ``step(a) -> (obs, r, terminated, truncated, info)``);
+        each environment step is ONE batched acting call over all seeds (agents whose episode has ended act on their last
+        observation and the action is dropped).  Returns the mean undiscounted return per seed, numpy [count]."""
+        import numpy as np
+
+        G = self.count
+        assert len(envs) == G, "one environment per stacked seed"
+        totals = np.zeros(G, np.float64)
+        for _ in range(n_episodes):
+            obs = np.stack([np.asarray(envs[g].reset()[0], np.float32) for g in range(G)])
+            live = np.ones(G, bool)
+            while live.any():
+                act = np.asarray(self.agent.sample(obs if G > 1 else obs[0], deterministic)).reshape(G, -1)
+                for g in range(G):
+                    if not live[g]:
+                        continue
+                    o, r, terminated, truncated, _ = envs[g].step(act[g])
+                    totals[g] += float(r)
+                    obs[g] = np.asarray(o, np.float32)
+                    live[g] = not (terminated or truncated)
+        return totals / n_episodes
+
     def gather_returns(self, local_returns: torch.Tensor) -> torch.Tensor:
+        """Per-seed evaluation returns of the whole population in global seed order (NCCL all-gather, ~1 KB per rank)."""
+        if not torch.is_tensor(local_returns):
+            local_returns = torch.as_tensor(local_returns, dtype=torch.float32)
+        if dist.is_initialized() and dist.get_backend() == "nccl":
+            local_returns = local_returns.to(self.agent.device)
         return gather_per_seed(local_returns, self.total_seeds)

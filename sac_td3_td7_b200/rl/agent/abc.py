@@ -64,9 +64,10 @@ class LazyScalar:
 class _DeviceView:
     """``__cuda_array_interface__`` holder for a float32 region of engine-owned device memory."""
 
-    def __init__(self, ptr: int, shape, owner):
+    def __init__(self, ptr: int, shape, owner, strides=None):
         self._owner = owner  # keeps the engine (and with it the memory) alive
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2, "strides": None}
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2,
+                                         "strides": tuple(strides) if strides else None}
 
 
 class Agent(ABC):
@@ -87,6 +88,7 @@ class Agent(ABC):
         self._dirty_host = True   # host modules newer than device blobs
         self._dirty_dev = False   # device blobs newer than host modules
         self._info_cache = {}
+        self._spilled = 0
         self._inbox = None
         self._create_engine()
         self._push()
@@ -129,10 +131,16 @@ class Agent(ABC):
         _lib.check(self._lib.b200rl_agent_write(self._h, net_id, 0, group, blob.ctypes.data, _stream()))
 
     def _read_blob(self, net_id, which=0, group=0):
+        """Packed blob of one network: parameters / exp_avg / exp_avg_sq / gradient (which = 0..3) of stacked seed
+        `group`, or of every stacked seed at once ([n_seeds, numel], one device-to-host copy) for group = -1."""
         numel, layers = self._layout(net_id)
-        blob = np.empty(numel, np.float32)
+        blob = np.empty(numel if group >= 0 else (self.n_seeds, numel), np.float32)
         _lib.check(self._lib.b200rl_agent_read(self._h, net_id, which, group, blob.ctypes.data, _stream()))
         return blob, layers
+
+    def _write_blob(self, net_id, which, blob, group=0):
+        blob = np.ascontiguousarray(blob, np.float32)
+        _lib.check(self._lib.b200rl_agent_write(self._h, net_id, which, group, blob.ctypes.data, _stream()))
 
     def _read_net_into(self, net_id, module, names, group=0):
         blob, layers = self._read_blob(net_id, 0, group)
@@ -158,8 +166,10 @@ class Agent(ABC):
         return self._mods[attr]
 
     def read_infos(self, first_step: int, count: int, seed: int = 0) -> np.ndarray:
-        """[count, len(INFO_KEYS)] info rows of stacked seed `seed` for updates first_step.. (1-based)."""
-        buf = np.empty((count, len(self.INFO_KEYS)), np.float32)
+        """[count, len(INFO_KEYS)] info rows of stacked seed `seed` for updates first_step.. (1-based); seed = -1:
+        every stacked seed, [n_seeds, count, len(INFO_KEYS)], from one strided device-to-host copy."""
+        shape = (count, len(self.INFO_KEYS)) if seed >= 0 else (self.n_seeds, count, len(self.INFO_KEYS))
+        buf = np.empty(shape, np.float32)
         _lib.check(self._lib.b200rl_agent_read_info(self._h, first_step, count, seed, buf.ctypes.data, _stream()))
         return buf
 
@@ -179,12 +189,42 @@ class Agent(ABC):
             self.sync_info = sync
         return out
 
-    def export_to(self, reference_agent) -> None:
-        """Copy the current networks into an agent of the REFERENCE's classes (same attribute names, same
-        ``state_dict`` keys), e.g. so that ``rl/replayer.py:43-45`` can render a policy trained here."""
+    def export_to(self, reference_agent, seed: int = 0) -> None:
+        """Copy the current networks of stacked seed `seed` into an agent of the REFERENCE's classes (same attribute
+        names, same ``state_dict`` keys), e.g. so that ``rl/replayer.py:43-45`` can render a policy trained here."""
+        mods = self.seed_modules(seed) if seed else None
         self._pull()
         for attr, _ in self.NETS:
-            getattr(reference_agent, attr).load_state_dict(getattr(self, attr).state_dict())
+            src = mods[attr] if mods else getattr(self, attr)
+            getattr(reference_agent, attr).load_state_dict(src.state_dict())
+
+    def mark_dirty(self) -> None:
+        """Tell the engine that the host-side modules (``agent.policy`` ...) were edited in place -- e.g.
+        ``agent.policy.load_state_dict(sd)`` -- so that the next update / act / copy uploads them first (stacked seed 0).
+        Without it the device blobs stay authoritative and the next access of a module re-reads them."""
+        self._pull()  # anything newer on the device first, so untouched modules are not clobbered
+        self._dirty_host = True
+
+    def import_from(self, reference_agent, seed: int = 0) -> None:
+        """Inverse of export_to: load the networks of an agent of the REFERENCE's classes (or of any object with the
+        same module attributes) into stacked seed `seed`.  Optimizer moments and counters keep their values."""
+        self._flush()
+        mods = {attr: getattr(reference_agent, attr) for attr, _ in self.NETS}
+        self.set_seed_weights(seed, mods)
+        self._dirty_dev = True
+
+    def seed_modules(self, seed: int) -> dict:
+        """Fresh host modules holding the CURRENT networks of stacked seed `seed` (attr -> nn.Module); the
+        ``.policy`` / ``.q1`` ... attributes always show seed 0."""
+        self._flush()
+        mods = self._fresh_modules_all()
+        for nid, (attr, names) in enumerate(self.NETS):
+            self._read_net_into(nid, mods[attr], names, group=seed)
+        return mods
+
+    def _fresh_modules_all(self) -> dict:
+        """One independent module per entry of NETS (targets are copies, not aliases)."""
+        return {attr: copy.deepcopy(self._mods[attr]) for attr, _ in self.NETS}
 
     def seed_population(self, base_seed: int) -> None:
         """Give every stacked seed its own initial networks: seed g is built exactly like a fresh
@@ -215,25 +255,41 @@ class Agent(ABC):
                 return float(v.value)
         return float(self._info_row(step)[col])
 
+    _RING = 1024          # kInfoRing of the engine
+    _SPILL_EVERY = 512    # updates between spills of the device ring into the host cache
+    _CACHE_ROWS = 1 << 18  # host rows kept (the reference's longest burst is 20 episodes x 1000 steps, run_w_checkpoint.py:145)
+
     def _info_row(self, step):
         """Row `step` (1-based train_ops count) of the device info ring; one D2H fetches every row
         from `step` to the newest, so reading a burst of infos costs a single sync."""
         row = self._info_cache.get(step)
         if row is None:
             n_calls = self._n_calls
-            if step <= n_calls - 1024:
-                raise _lib.B200RLError("this update's info was overwritten in the 1024-entry device ring; read it sooner or use sync_info=True")
-            cols = len(self.INFO_KEYS)
-            count = n_calls - step + 1
-            buf = np.empty((count, cols), np.float32)
-            _lib.check(self._lib.b200rl_agent_read_info(self._h, step, count, 0, buf.ctypes.data, _stream()))
-            for i in range(count):
-                self._info_cache[step + i] = buf[i]
-            if len(self._info_cache) > 4096:
-                for k in sorted(self._info_cache)[:-2048]:
-                    del self._info_cache[k]
+            if step <= n_calls - self._RING:
+                raise _lib.B200RLError("this update's info is no longer in the device ring nor in the host cache")
+            self._fetch_infos(step, n_calls - step + 1)
             row = self._info_cache[step]
         return row
+
+    def _fetch_infos(self, first, count):
+        cols = len(self.INFO_KEYS)
+        buf = np.empty((count, cols), np.float32)
+        _lib.check(self._lib.b200rl_agent_read_info(self._h, first, count, 0, buf.ctypes.data, _stream()))
+        for i in range(count):
+            self._info_cache[first + i] = buf[i]
+        if len(self._info_cache) > self._CACHE_ROWS:
+            for k in sorted(self._info_cache)[: len(self._info_cache) - self._CACHE_ROWS // 2]:
+                del self._info_cache[k]
+
+    def _spill_infos(self):
+        """Copy the not yet cached tail of the device ring to the host before it wraps: the runners evaluate the
+        LazyScalars of a whole burst only afterwards (run_w_checkpoint.py:145-147 then run.py:53-84), which may be
+        far more than 1024 updates later.  One small D2H + sync per 512 updates."""
+        n = self._n_calls
+        first = max(self._spilled + 1, n - self._RING + 1, 1)
+        if n >= first:
+            self._fetch_infos(first, n - first + 1)
+        self._spilled = n
 
     # ------------------------------------------------------------------ reference contract
     def make_optimizers(self, *a, **k) -> None:
@@ -274,6 +330,7 @@ class Agent(ABC):
         new._h = None
         new._inbox = None
         new._info_cache = {}
+        new._spilled = new._n_calls
         new._create_engine()
         _lib.check(new._lib.b200rl_agent_copy_from(new._h, self._h, 1, _stream()))
         new._dirty_dev, new._dirty_host = True, False
@@ -286,9 +343,12 @@ class Agent(ABC):
         d = {k: v for k, v in self.__dict__.items() if k not in ("_h", "_lib", "_info_cache", "_inbox")}
         extra = {}
         if self._h:
+            self._flush()
             for nid, (attr, _) in enumerate(self.NETS):
-                if attr in self.TRAINED:
-                    extra[attr] = (self._read_blob(nid, 1)[0], self._read_blob(nid, 2)[0])
+                # every stacked seed: one [n_seeds, numel] copy per tensor kind (parameters of all networks; Adam
+                # moments of the trained ones)
+                kinds = (0, 1, 2) if attr in self.TRAINED else (0,)
+                extra[attr] = tuple(self._read_blob(nid, w, -1)[0] for w in kinds)
             n_runs, steps = C.c_int64(), (C.c_int64 * 3)()
             _lib.check(self._lib.b200rl_agent_get_counters(self._h, C.byref(n_runs), steps))
             extra["__counters__"] = (n_runs.value, list(steps))
@@ -305,14 +365,19 @@ class Agent(ABC):
         self._push()
         for nid, (attr, _) in enumerate(self.NETS):
             if attr in extra:
-                m, v = extra[attr]
-                _lib.check(self._lib.b200rl_agent_write(self._h, nid, 1, 0, m.ctypes.data, _stream()))
-                _lib.check(self._lib.b200rl_agent_write(self._h, nid, 2, 0, v.ctypes.data, _stream()))
+                for w, blob in enumerate(extra[attr]):
+                    blob = np.asarray(blob, np.float32)
+                    if blob.ndim == 1:  # pickles written before populations were persisted: seed 0 only, (m, v)
+                        self._write_blob(nid, w + 1, blob, 0)
+                    else:
+                        self._write_blob(nid, w, blob, -1)
         if "__counters__" in extra:
             n_runs, steps = extra["__counters__"]
             _lib.check(self._lib.b200rl_agent_set_counters(self._h, n_runs, (C.c_int64 * 3)(*steps), _stream()))
             self._n_calls = n_runs
+        self._spilled = self._n_calls
         self._restore_extra_state(extra)
+        self._dirty_dev, self._dirty_host = True, False
 
     def _extra_state(self):
         return {}
@@ -340,15 +405,18 @@ class Agent(ABC):
         this agent is the buffer's sink, so that train_ops(batch) needs no staging copy."""
         ss, ac, rw, nd, gs = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
         _lib.check(self._lib.b200rl_agent_io(self._h, C.byref(ss), C.byref(ac), C.byref(rw), C.byref(nd), C.byref(gs)))
-        B, S, A = self.batch_size, self.state_dim, self.action_dim
-        view = lambda ptr, shape: torch.as_tensor(_DeviceView(ptr, shape, self), device=self.device)  # noqa: E731
-        return {"state": view(ss.value, (B, S)), "action": view(ac.value, (B, A)), "reward": view(rw.value, (B, 1)),
-                "next_state": view(ss.value + 4 * B * S, (B, S)), "done": view(nd.value, (B, 1))}
+        B, S, A, G = self.batch_size, self.state_dim, self.action_dim, self.n_seeds
+        if G == 1:
+            view = lambda ptr, d: torch.as_tensor(_DeviceView(ptr, (B, d), self), device=self.device)  # noqa: E731
+        else:  # [n_seeds, B, d] views strided by the engine's per-seed arena
+            view = lambda ptr, d: torch.as_tensor(_DeviceView(ptr, (G, B, d), self, strides=(4 * gs.value, 4 * d, 4)), device=self.device)  # noqa: E731
+        return {"state": view(ss.value, S), "action": view(ac.value, A), "reward": view(rw.value, 1),
+                "next_state": view(ss.value + 4 * B * S, S), "done": view(nd.value, 1)}
 
     def _adopt_sink(self, replay_buffer):
-        if replay_buffer is None or self.n_seeds != 1 or not getattr(replay_buffer, "zero_copy", False):
+        if replay_buffer is None or not getattr(replay_buffer, "zero_copy", False):
             return
-        if getattr(replay_buffer, "n_seeds", 1) != 1 or not hasattr(replay_buffer, "_sink"):
+        if getattr(replay_buffer, "n_seeds", 1) != self.n_seeds or not hasattr(replay_buffer, "_sink"):
             return
         cur = replay_buffer._sink() if replay_buffer._sink is not None else None
         if cur is not self:
@@ -361,8 +429,12 @@ class Agent(ABC):
             return batch  # sampled straight into the engine's input buffers
         dev = self.device
         t = {k: torch.as_tensor(v, dtype=torch.float32).to(dev, non_blocking=True).contiguous() for k, v in batch.items()}
-        _lib.check(self._lib.b200rl_agent_stage_batch(self._h, 0, t["state"].data_ptr(), t["action"].data_ptr(), t["reward"].data_ptr(),
-                                                      t["next_state"].data_ptr(), t["done"].data_ptr(), _stream()))
+        G, B = self.n_seeds, self.batch_size
+        for g in range(G):  # stacked seeds: [n_seeds, B, dim] tensors, one seed's slice each
+            off = {k: 4 * g * B * (v.numel() // (G * B)) for k, v in t.items()}
+            _lib.check(self._lib.b200rl_agent_stage_batch(self._h, g, t["state"].data_ptr() + off["state"], t["action"].data_ptr() + off["action"],
+                                                          t["reward"].data_ptr() + off["reward"], t["next_state"].data_ptr() + off["next_state"],
+                                                          t["done"].data_ptr() + off["done"], _stream()))
         return t
 
     def _update(self, replay_buffer, noise, sink=None):
@@ -375,14 +447,25 @@ class Agent(ABC):
         _lib.check(self._lib.b200rl_agent_update(self._h, rh, nz.data_ptr() if nz is not None else None, _stream()))
         self._n_calls += 1
         self._dirty_dev = True
+        if self._n_calls - self._spilled >= self._SPILL_EVERY:
+            self._spill_infos()
 
     def train_ops_n(self, n_ops: int, replay_buffer) -> list[dict]:
         """``run_train_ops(n_ops=k)`` (run.py:87-96) without leaving the device: k x {sample, update}."""
         self._flush()
         first = self._n_calls + 1
+        n_ops = int(n_ops)
         actor_flags = [self._actor_step(first + i) for i in range(n_ops)]
-        _lib.check(self._lib.b200rl_agent_update_n(self._h, replay_buffer._h, int(n_ops), _stream()))
-        self._n_calls += n_ops
+        done = 0
+        while done < n_ops:  # bursts longer than the device info ring run in pieces with a spill between them
+            room = self._SPILL_EVERY - (self._n_calls - self._spilled)
+            if room <= 0:
+                self._spill_infos()
+                room = self._SPILL_EVERY
+            k = min(n_ops - done, room)
+            _lib.check(self._lib.b200rl_agent_update_n(self._h, replay_buffer._h, k, _stream()))
+            self._n_calls += k
+            done += k
         self._dirty_dev = True
         replay_buffer._last_batch = self.batch_size
         return [self._info_dict(first + i, actor_flags[i]) for i in range(n_ops)]
@@ -398,10 +481,30 @@ class Agent(ABC):
 
     # ------------------------------------------------------------------ acting
     def _policy_out(self, state) -> np.ndarray:
+        """Raw policy output for one observation per stacked seed, host to host through ONE kernel
+        (b200rl_agent_act_host).  `state`: [S] (a single agent, or the same observation for every stacked seed) or
+        [n_seeds, S]; returns [A_out] for a single agent, [n_seeds, A_out] for a population."""
         self._flush()
-        if not isinstance(state, torch.Tensor):
-            state = torch.as_tensor(np.asarray(state), dtype=torch.float32)
-        obs = state.reshape(1, -1).to(self.device, non_blocking=True).contiguous()
-        out = torch.empty((1, self._act_out_dim), device=self.device)
+        G, S = self.n_seeds, self.state_dim
+        if isinstance(state, torch.Tensor):
+            state = state.detach().cpu().numpy()
+        obs = np.asarray(state, np.float32)
+        if obs.size == S:
+            obs = np.broadcast_to(obs.reshape(1, S), (G, S))
+        elif obs.shape != (G, S):
+            raise ValueError(f"observation must have shape ({S},) or ({G}, {S}), got {obs.shape}")
+        obs = np.ascontiguousarray(obs)
+        out = np.empty((G, self._act_out_dim), np.float32)
+        _lib.check(self._lib.b200rl_agent_act_host(self._h, obs.ctypes.data, out.ctypes.data, _stream()))
+        return out[0] if G == 1 else out
+
+    def policy_out_device(self, obs: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """The same forward on device tensors, asynchronously on the current stream: obs [n_seeds, S] (CUDA, fp32,
+        contiguous) -> [n_seeds, A_out].  For vectorised simulators that keep observations on the GPU."""
+        self._flush()
+        G = self.n_seeds
+        obs = obs.to(self.device, torch.float32).reshape(G, self.state_dim).contiguous()
+        if out is None:
+            out = torch.empty((G, self._act_out_dim), device=self.device)
         _lib.check(self._lib.b200rl_agent_act(self._h, obs.data_ptr(), out.data_ptr(), _stream()))
-        return out.cpu().numpy()[0]
+        return out

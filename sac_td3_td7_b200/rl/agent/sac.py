@@ -71,16 +71,16 @@ class SAC(_MlpAgent):
     def _extra_state(self):
         if not self.auto_tmp_mode:
             return {}
-        out = np.empty((3, 1), np.float32)
+        out = np.empty((3, self.n_seeds), np.float32)  # log-temperature, exp_avg, exp_avg_sq of every stacked seed
         for w in range(3):
-            _lib.check(self._lib.b200rl_agent_read(self._h, 5, w, 0, out[w].ctypes.data, _stream()))
+            _lib.check(self._lib.b200rl_agent_read(self._h, 5, w, -1, out[w].ctypes.data, _stream()))
         return {"__tmp__": out}
 
     def _restore_extra_state(self, extra):
         if "__tmp__" in extra:
             for w in range(3):
-                v = np.ascontiguousarray(extra["__tmp__"][w], np.float32)
-                _lib.check(self._lib.b200rl_agent_write(self._h, 5, w, 0, v.ctypes.data, _stream()))
+                v = np.ascontiguousarray(extra["__tmp__"][w], np.float32).reshape(-1)
+                _lib.check(self._lib.b200rl_agent_write(self._h, 5, w, -1 if v.size == self.n_seeds and self.n_seeds > 1 else 0, v.ctypes.data, _stream()))
 
     def _info_dict(self, step: int, actor: bool) -> dict:
         vals = [LazyScalar(self, step, c) for c in range(6)]
@@ -106,13 +106,13 @@ class SAC(_MlpAgent):
     @torch.no_grad()
     def sample(self, state, deterministic: bool = False, **kwargs) -> np.ndarray:
         """sac.py:131-159"""
-        out = self._policy_out(state)
+        out = self._policy_out(state)  # [2A], or [n_seeds, 2A] for a population
         A = self.action_dim
-        mean, log_std = out[:A], np.clip(out[A:], self.min_log_std, self.max_log_std)
+        mean, log_std = out[..., :A], np.clip(out[..., A:], self.min_log_std, self.max_log_std)
         if deterministic:
             action = np.tanh(mean)
         else:
-            action = np.tanh(mean + torch.empty(A).normal_().numpy() * np.exp(log_std))
+            action = np.tanh(mean + torch.empty(mean.shape).normal_().numpy() * np.exp(log_std))
         return action * self.action_scale + self.action_bias
 
     def __repr__(self) -> str:

@@ -98,9 +98,10 @@ class TD7(Agent):
     def n_runs(self) -> int:
         return self._n_calls
 
-    def _range(self):
-        out = np.empty(4, np.float32)
-        _lib.check(self._lib.b200rl_td7_value_range(self._h, 0, out.ctypes.data, _stream()))
+    def _range(self, seed: int = 0):
+        """[value_max, value_min, value_target_max, value_target_min] of one stacked seed; seed = -1: [n_seeds, 4]."""
+        out = np.empty(4 if seed >= 0 else (self.n_seeds, 4), np.float32)
+        _lib.check(self._lib.b200rl_td7_value_range(self._h, seed, out.ctypes.data, _stream()))
         return out
 
     value_max = property(lambda self: float(self._range()[0]))
@@ -109,12 +110,12 @@ class TD7(Agent):
     value_target_min = property(lambda self: float(self._range()[3]))
 
     def _extra_state(self):
-        return {"__range__": self._range()}
+        return {"__range__": self._range(-1)}
 
     def _restore_extra_state(self, extra):
         if "__range__" in extra:
             r = np.ascontiguousarray(extra["__range__"], np.float32)
-            _lib.check(self._lib.b200rl_td7_set_value_range(self._h, 0, r.ctypes.data, _stream()))
+            _lib.check(self._lib.b200rl_td7_set_value_range(self._h, -1 if r.ndim == 2 else 0, r.ctypes.data, _stream()))
 
     def _actor_step(self, call_index: int) -> bool:
         return call_index % self.policy_freq == 0  # td7.py:295,319: n_runs is incremented first

@@ -45,7 +45,13 @@ class _DeviceRing(BaseReplayMemory):
         self.ptr = 0
         self.size = 0
         self._last_batch = 0
-        self._row = np.zeros((1, self.row_stride), np.float32)
+        # lap.py:35 runs on the device: the append kernel divides / subtracts in IEEE fp32 (numpy's result for fp32 actions)
+        A = self.action_dim
+        self._scale32 = np.ascontiguousarray(np.broadcast_to(np.asarray(self.action_scale, np.float32), (A,)))
+        self._bias32 = np.ascontiguousarray(np.broadcast_to(np.asarray(self.action_bias, np.float32), (A,)))
+        _lib.check(self._lib.b200rl_replay_set_action_norm(self._h, self._scale32.ctypes.data, self._bias32.ctypes.data))
+        self._rew1, self._nd1 = np.zeros(1, np.float32), np.zeros(1, np.float32)
+        self._rew1_p, self._nd1_p = self._rew1.ctypes.data, self._nd1.ctypes.data
         # zero-copy hand-off: once an agent has trained from this buffer (train_ops(batch, replay_buffer=self)),
         # sample() writes straight into that agent's fixed input buffers and returns tensors that ALIAS them --
         # the next sample() overwrites them.  zero_copy=False restores private tensors per call.
@@ -74,18 +80,47 @@ class _DeviceRing(BaseReplayMemory):
         return rows
 
     def append(self, transition: list[Any], seed: int = 0) -> None:
-        """lap.py:31-43 -- one transition [obs, action(env units), reward, next_obs, notdone]."""
+        """lap.py:31-43 -- one transition [obs, action(env units), reward, next_obs, notdone].
+
+        One C call: the library packs the row into a pinned staging slot and ONE kernel copies it into the ring,
+        normalises the action (``a / scale - bias``, lap.py:35), writes the priority and repairs the sum tree.  fp32
+        actions (what ``agent.sample`` and gym's ``action_space.sample`` produce) are normalised on the device in IEEE fp32
+        -- the value numpy computes; any other dtype is normalised here the way numpy would and stored."""
         assert len(transition) == 5
         obs, action, reward, next_obs, float_done = transition
-        action = action / self.action_scale - self.action_bias  # (sic) lap.py:35
-        S, A = self.state_dim, self.action_dim
-        row = self._row
-        row[0, :S] = obs
-        row[0, S:S + A] = action
-        row[0, S + A] = reward
-        row[0, S + A + 1] = float_done
-        row[0, S + A + 2:2 * S + A + 2] = next_obs
-        self.append_rows(row, seed)
+        action = np.asarray(action)
+        raw = action.dtype == np.float32
+        if not raw:
+            action = np.asarray(action / self.action_scale - self.action_bias, np.float32)  # (sic) lap.py:35
+        obs = np.ascontiguousarray(obs, np.float32)
+        action = np.ascontiguousarray(action)
+        next_obs = np.ascontiguousarray(next_obs, np.float32)
+        assert obs.size == self.state_dim and next_obs.size == self.state_dim and action.size == self.action_dim
+        self._rew1[0], self._nd1[0] = reward, float_done
+        _lib.check(self._lib.b200rl_replay_append_transitions(self._h, seed, 1, obs.ctypes.data, action.ctypes.data, self._rew1_p, next_obs.ctypes.data,
+                                                              self._nd1_p, int(raw), _stream()))
+        if seed == 0:
+            self.ptr = (self.ptr + 1) % self.replay_buffer_size
+            self.size = min(self.size + 1, self.replay_buffer_size)
+
+    def append_population(self, obs, action, reward, next_obs, float_done) -> None:
+        """One environment step of every stacked seed (rl/rollout.py:45 once per seed) in ONE launch: obs / next_obs
+        [n_seeds, S], action [n_seeds, A] in environment units, reward / float_done [n_seeds].  With ``share_rows`` the
+        store keeps seed 0's transition and every seed's priorities / cursor advance."""
+        G = self.n_seeds
+        action = np.asarray(action)
+        raw = action.dtype == np.float32
+        if not raw:
+            action = np.asarray(action / self.action_scale - self.action_bias, np.float32)
+        obs = np.ascontiguousarray(obs, np.float32).reshape(G, self.state_dim)
+        action = np.ascontiguousarray(action).reshape(G, self.action_dim)
+        next_obs = np.ascontiguousarray(next_obs, np.float32).reshape(G, self.state_dim)
+        reward = np.ascontiguousarray(reward, np.float32).reshape(G)
+        float_done = np.ascontiguousarray(float_done, np.float32).reshape(G)
+        _lib.check(self._lib.b200rl_replay_append_transitions(self._h, 0, G, obs.ctypes.data, action.ctypes.data, reward.ctypes.data, next_obs.ctypes.data,
+                                                              float_done.ctypes.data, int(raw), _stream()))
+        self.ptr = (self.ptr + 1) % self.replay_buffer_size
+        self.size = min(self.size + 1, self.replay_buffer_size)
 
     def append_rows(self, rows, seed: int = 0) -> None:
         """Bulk append of packed rows (numpy / CPU tensor -> H2D, CUDA tensor -> D2D).
@@ -133,7 +168,7 @@ class _DeviceRing(BaseReplayMemory):
             u_ptr = None
             if u is not None:
                 u = torch.as_tensor(u, dtype=torch.float32).to(self.device).contiguous()
-                assert u.numel() == B
+                assert u.numel() == G * B
                 u_ptr = u.data_ptr()
             _lib.check(self._lib.b200rl_replay_sample_to_agent(self._h, sink._h, B, u_ptr, _stream()))
             self._last_batch = B

@@ -38,3 +38,17 @@ def dev(request):
     d = devlib.Dev(request.param)
     yield d
     d.free_all()
+
+
+@pytest.fixture(params=["mma", "ffma"])
+def gemm_path(request, dev):
+    """Every GEMM-family test runs on both product loops of the small-tile kernel: 3xTF32 on the tensor cores (the
+    default) and fp32 FFMA.  The host emulation has only the FFMA loop."""
+    if dev.backend == "emu":
+        if request.param == "mma":
+            pytest.skip("the host emulation runs the FFMA loop only")
+        yield
+        return
+    dev.lib.b200rl_set_mma(1 if request.param == "mma" else 0)
+    yield
+    dev.lib.b200rl_set_mma(-1)

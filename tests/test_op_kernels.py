@@ -14,6 +14,9 @@ import torch.nn.functional as F
 from sac_td3_td7_b200 import _lib
 
 
+pytestmark = pytest.mark.usefixtures("gemm_path")  # both product loops of the small-tile kernel (conftest.py)
+
+
 def nerr(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
