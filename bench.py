@@ -3,18 +3,25 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
 
-One "step" = one update = ``replay.sample(256)`` + ``agent.train_ops(...)`` incl. priority write-back
-and the amortised delayed actor step / target sync.  Prints ONE JSON line (rank 0).
+With no --workload the line measures BASELINE.json configs[4] -- the north star's population: TD7 on Ant-v4 shapes,
+256 independent seeds stacked per GPU (2 048 on 8 GPUs), 1M-row LAP replay per seed:
 
-* value   : updates/s with everything resident on the device (burst API ``train_ops_n``), timed with
-            CUDA events, max over ranks; whole-job aggregate over N GPUs (independent agents per GPU:
-            the per-agent update does not shard -- "replicas", weak scaling).
-* e2e     : the same metric through the reference-facing Python API with HOST data in the loop: every
-            step appends one transition from pinned host memory (H2D), samples, runs ``train_ops`` and
-            reads the info floats back (D2H + sync), as ``rl/runner/run.py:160-171`` drives it.
-* roofline: the dominant kernel (grouped FFMA GEMM) and, separately, the HBM-bound LAP tile-sum kernel.
-* cpu_baseline / --impl reference: the oracle port of the reference's CPU update loop (the reference is
-            pure Python and cannot travel to the GPU box), all host threads, bounded sample.
+* value   : agent-updates/s.  One "step" = one stacked update = every seed of this GPU does ``sample(256)`` +
+            ``train_ops`` (priority write-back, amortised actor step / target sync).  K steps through the burst API
+            (``train_ops_n``), everything resident in HBM, CUDA events, max over ranks, whole-job aggregate.
+* e2e     : the same through the reference-facing Python API with HOST data in the loop: per step one transition per seed
+            appended from pinned host memory (H2D, read by the append kernel), ``sample``, ``train_ops``, every seed's
+            ``train/q_fn`` read back (D2H), and every 10th step an all-gather of a per-seed metric over NCCL.
+* single_agent (N = 1 only): sub-records for ``td7_humanoid_1M`` (the >= 100x target: value, e2e, the CPU arm at 1 thread
+            and at all threads, ratio against the better), ``td7_halfcheetah_1M`` (configs[1]), ``sac_walker2d_1M``
+            (configs[2]) and ``td7_humanoid_pop256`` (configs[3]).  Each times >= 2 000 updates whatever --steps says
+            (a handful of 0.2 ms updates is not a measurement window).
+* roofline: the dominant kernel of the stacked update (persistent tcgen05 weight-gradient + Adam launch) against the
+            measured HBM peak on SURVEY 8(d)'s algorithmic bytes; ``roofline_replay``: the LAP tree-walk + gather kernel.
+* cpu_baseline / --impl reference: the reference's own CPU loop (``rl/runner/run.py:87-96``: ``LAPReplayMemory.sample`` +
+            ``TD7.train_ops``) from the staged unmodified copy ``baseline/_ref`` under ``oracle/gym_stub`` when present
+            (kind "reference"), else the oracle port (kind "port"); 1 thread and all threads, the better is the value.
+            The reference runs seeds one after the other (scripts/td7_exp.sh:1-4), so its agent-updates/s is one agent's.
 """
 from __future__ import annotations
 
@@ -31,18 +38,22 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (algo, env, prioritized, seeds stacked per GPU, buffer rows)
-    "td7_halfcheetah_1M": ("TD7", "HalfCheetah-v4", True, 1, 1_000_000),
-    "td7_humanoid_1M": ("TD7", "Humanoid-v4", True, 1, 1_000_000),
-    "td7_ant_1M": ("TD7", "Ant-v4", True, 1, 1_000_000),
-    "td3_hopper_1M": ("TD3", "Hopper-v4", False, 1, 1_000_000),
-    "sac_walker2d_1M": ("SAC", "Walker2d-v4", False, 1, 1_000_000),
-    "td7_ant_pop256": ("TD7", "Ant-v4", True, 256, 1_000_000),
-    "td7_humanoid_pop256": ("TD7", "Humanoid-v4", True, 256, 200_000),
+    # name: (algo, env, prioritized, seeds stacked per GPU, buffer rows, one row store shared by the stacked seeds)
+    "td7_halfcheetah_1M": ("TD7", "HalfCheetah-v4", True, 1, 1_000_000, False),
+    "td7_humanoid_1M": ("TD7", "Humanoid-v4", True, 1, 1_000_000, False),
+    "td7_ant_1M": ("TD7", "Ant-v4", True, 1, 1_000_000, False),
+    "td3_hopper_1M": ("TD3", "Hopper-v4", False, 1, 1_000_000, False),
+    "sac_walker2d_1M": ("SAC", "Walker2d-v4", False, 1, 1_000_000, False),
+    # 256 x 1M Ant rows of 256 B = 65.5 GB of private row stores + 1 GB of priorities per GPU
+    "td7_ant_pop256": ("TD7", "Ant-v4", True, 256, 1_000_000, False),
+    # 256 x 1M Humanoid rows would be 790 GB: one shared 200k-row store (618 MB), private priorities
+    "td7_humanoid_pop256": ("TD7", "Humanoid-v4", True, 256, 200_000, True),
 }
-DEFAULT_WORKLOAD = "td7_halfcheetah_1M"  # BASELINE.json configs[1]
+DEFAULT_WORKLOAD = "td7_ant_pop256"  # BASELINE.json configs[4], the north star's population (256 seeds per GPU)
 ENV_DIMS = {"Hopper-v4": (11, 3), "HalfCheetah-v4": (17, 6), "Walker2d-v4": (17, 6), "Ant-v4": (27, 8), "Humanoid-v4": (376, 17)}
 BATCH = 256
+MIN_SINGLE_UPDATES = 2000
+METRIC = "gradient updates/sec (batch 256) per agent and agent-updates/sec at 1/2/4/8 B200"
 
 
 def algorithmic_gflop(algo: str, S: int, A: int, B: int = BATCH, H: int = 256, Z: int = 256) -> float:
@@ -65,58 +76,121 @@ def algorithmic_gflop(algo: str, S: int, A: int, B: int = BATCH, H: int = 256, Z
     return 2.0 * macs * B / 1e9
 
 
+def algorithmic_mbytes_stacked(S: int, A: int, H: int = 256, Z: int = 256) -> float:
+    """SURVEY.md 8(d) "Algorithmic bytes (stacked update)", TD7, per seed-update, fp32: trained parameters with Adam state
+    24 B/param (encoder, q1, q2 every update; policy every 2nd), frozen nets read once 4 B/param."""
+    enc = (S * H + H) + 2 * (H * H + H) + ((Z + A) * H + H) + 2 * (H * H + H)
+    pol = (S * H + H) + ((Z + H) * H + H) + (H * H + H) + (H * A + A)
+    q = ((S + A) * H + H) + ((2 * Z + H) * H + H) + (H * H + H) + (H + 1)
+    return (24.0 * (enc + 2 * q + 0.5 * pol) + 4.0 * (2 * enc + 2 * q)) / 1e6
+
+
+def workload_config(name: str, world: int) -> dict:
+    algo, env, prio, seeds, rows, share = WORKLOADS[name]
+    S, A = ENV_DIMS[env]
+    return {"workload": name, "algo": algo, "env": env, "obs_dim": S, "act_dim": A, "batch": BATCH, "buffer_rows": rows,
+            "replay": "LAP" if prio else "uniform", "seeds_per_gpu": seeds, "total_seeds": seeds * world,
+            "row_store": "shared by the stacked seeds (private priorities)" if share else "private per seed",
+            "parallelism": f"seeds sharded over {world} GPU(s), no data-path collective; NCCL all-gather of per-seed metrics only",
+            "l2": "replay rows and, for stacked seeds, weights + Adam state exceed L2 (inputs larger than L2)"}
+
+
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_updates_per_s(workload: str, budget_s: float, steps: int | None = None, warmup: int = 5):
-    """The reference's CPU update loop (oracle port: same torch ops in the same order, pinned bit-exact to
-    the reference by tests/test_oracle_golden.py) on this host, all threads."""
+def _ref_dir():
+    d = os.path.join(ROOT, "baseline", "_ref")
+    return d if os.path.isdir(os.path.join(d, "rl")) else None
+
+
+def _make_cpu_loop(workload: str):
+    """(step_fn, kind): one CPU update of the workload's single agent -- the unmodified reference when staged, else the port."""
+    import numpy as np
     import torch
 
-    from oracle import agents as oagents
-    from oracle import replay as oreplay
-
-    algo, env, prio, _, rows = WORKLOADS[workload]
-    # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1 to its workers)
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    algo, env, prio, _, rows, _ = WORKLOADS[workload]
+    ref = _ref_dir()
     torch.manual_seed(0)
-    agent = {"TD7": oagents.OracleTD7, "TD3": oagents.OracleTD3, "SAC": oagents.OracleSAC}[algo](env, use_lap=prio)
-    buf = (oreplay.OracleLAP if prio else oreplay.OracleUniform)(rows, env)
-    buf.fill_synthetic(rows, seed=0)
-    for _ in range(warmup):
-        agent.train_ops(buf.sample(BATCH), replay_buffer=buf)
-    n, t0 = 0, time.perf_counter()
-    while True:
-        agent.train_ops(buf.sample(BATCH), replay_buffer=buf)
-        n += 1
-        el = time.perf_counter() - t0
-        if (steps is not None and n >= steps) or (steps is None and el >= budget_s):
-            break
-        if el > 180:
-            break
-    return n / el, n, el, torch.get_num_threads()
+    if ref is not None:
+        from oracle import gym_stub
+
+        gym_stub.import_reference(ref)
+        from rl.agent import SAC, TD3, TD7  # noqa: PLC0415  (the reference's own classes)
+        from rl.replay_memory import LAPReplayMemory, SimpleReplayMemory  # noqa: PLC0415
+
+        agent = {"TD7": TD7, "TD3": TD3, "SAC": SAC}[algo](env, **({} if algo == "SAC" else {"use_lap": prio}))
+        buf = (LAPReplayMemory if prio else SimpleReplayMemory)(rows, env)
+        g = np.random.default_rng(0)  # BASELINE.md section 2 synthetic contents, written straight into the reference's arrays
+        for lo in range(0, rows, 65536):
+            hi = min(rows, lo + 65536)
+            buf.state[lo:hi] = g.standard_normal((hi - lo, buf.state.shape[1]), dtype=np.float32)
+            buf.action[lo:hi] = g.random((hi - lo, buf.action.shape[1]), dtype=np.float32) * 2.0 - 1.0
+            buf.reward[lo:hi] = g.standard_normal((hi - lo, 1), dtype=np.float32)
+            buf.next_state[lo:hi] = g.standard_normal((hi - lo, buf.state.shape[1]), dtype=np.float32)
+            buf.float_done[lo:hi] = (g.random((hi - lo, 1), dtype=np.float32) < 0.99)
+        if prio:
+            buf.priority[:rows] = 1.0
+        buf.size, buf.ptr = rows, 0
+        kind = "reference"
+    else:
+        from oracle import agents as oagents
+        from oracle import replay as oreplay
+
+        agent = {"TD7": oagents.OracleTD7, "TD3": oagents.OracleTD3, "SAC": oagents.OracleSAC}[algo](env, use_lap=prio)
+        buf = (oreplay.OracleLAP if prio else oreplay.OracleUniform)(rows, env)
+        buf.fill_synthetic(rows, seed=0)
+        kind = "port"
+
+    def step():
+        agent.train_ops(buf.sample(BATCH), replay_buffer=buf)  # rl/runner/run.py:92-95
+
+    return step, kind
+
+
+def cpu_updates_per_s(workload: str, budget_s: float, updates: int | None = None, warmup: int = 5, thread_settings=None):
+    """Times the CPU loop at each thread setting; returns {"value", "cores", "kind", "sample", "by_threads"}: value = the
+    better setting ("1 thread and all threads, take the better")."""
+    import torch
+
+    ncpu = max(1, os.cpu_count() or 1)
+    settings = thread_settings or ([1, ncpu] if ncpu > 1 else [1])
+    step, kind = _make_cpu_loop(workload)
+    by, best = {}, None
+    for th in settings:
+        torch.set_num_threads(th)  # (also under torchrun, which exports OMP_NUM_THREADS=1 to its workers)
+        for _ in range(warmup):
+            step()
+        n, t0 = 0, time.perf_counter()
+        while True:
+            step()
+            n += 1
+            el = time.perf_counter() - t0
+            if (updates is not None and n >= updates) or (updates is None and el >= budget_s / len(settings)) or el > 120:
+                break
+        by[str(th)] = {"updates_per_s": n / el, "updates": n, "seconds": el}
+        if best is None or n / el > best[0]:
+            best = (n / el, th, n, el)
+    ups, th, n, el = best
+    return {"value": ups, "unit": "updates/s", "cores": th, "kind": kind, "by_threads": by,
+            "sample": f"{n} updates of {'the unmodified reference (baseline/_ref, fake gymnasium)' if kind == 'reference' else 'the oracle port of the reference loop'}"
+                      f" on {workload}'s single agent, torch {torch.__version__} CPU, best of threads {settings} = {th} (os.cpu_count={ncpu}), {el:.1f}s"}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-
-    # A reference-arm step is a bounded sample of the workload: `per_step` consecutive updates, sized so that K steps hold
-    # at least ~600 updates (8-10 s of CPU work; a handful of 14 ms updates would time thread wake-ups, not the loop) and
-    # the whole run stays under a few minutes.  The default run (no --steps) is a 20 s sample.
-    warm = max(args.warmup, 10)
-    per_step = max(1, -(-600 // args.steps)) if args.steps_given else 1
-    ups, n, el, threads = cpu_updates_per_s(args.workload, budget_s=20.0, steps=args.steps * per_step if args.steps_given else None, warmup=warm)
-    algo, env, prio, seeds, rows = WORKLOADS[args.workload]
-    k_steps = args.steps if args.steps_given else n
+    # A reference-arm step is a bounded sample of the workload: `per_step` consecutive updates of one agent, sized so that the
+    # K steps hold a few hundred updates per thread setting and the whole run stays within a few minutes.
+    K, W = args.steps, args.warmup
+    per_step = max(1, -(-300 // K))
+    cpu = cpu_updates_per_s(args.workload, budget_s=40.0, updates=K * per_step if args.steps_given else None, warmup=max(W, 5))
     line = {
-        "impl": "reference", "metric": "gradient updates/sec (batch 256) per agent", "value": ups, "unit": "updates/s", "n_gpus": args.gpus,
-        "steps": k_steps, "updates_per_step": n / k_steps, "warmup": warm, "ms_per_step": 1e3 * el / k_steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "algo": algo, "env": env, "batch": BATCH, "buffer_rows": rows, "replay": "LAP" if prio else "uniform"},
-        "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": threads, "kind": "port",
-                         "sample": f"{n} updates of the oracle port (torch {torch.__version__} CPU, {threads} threads, os.cpu_count={os.cpu_count()}) in {el:.1f}s"},
-        "e2e": {"value": ups, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "updates/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "updates_per_step": per_step if args.steps_given else None,
+        "ms_per_step": 1e3 * per_step / cpu["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.workload, args.gpus),
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference trains the seeds of a population one after the other (scripts/td7_exp.sh:1-4): its agent-updates/s is one agent's updates/s",
     }
     print(json.dumps(line), flush=True)
 
@@ -133,10 +207,9 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             self.p = None
 
-    def stop(self, timed=None, probe=None):
-        """Median SM clock and the throttle reasons seen.  `timed` = (t0, t1) wall-clock bounds of the timed region: its
-        samples are the ones reported; when the region is shorter than the 100 ms sampling period and holds none, the
-        samples of the whole loaded window (warm-up + timed + end-to-end loop) are reported instead, and `window` says so."""
+    def stop(self, timed=None):
+        """Median SM clock and the throttle reasons seen inside `timed` = (t0, t1) wall-clock bounds (the timed regions);
+        when they hold no sample (shorter than the 100 ms sampling period) the whole loaded window is reported and says so."""
         import datetime
 
         if self.p is None:
@@ -157,21 +230,17 @@ class ClockSampler:
             try:
                 ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
             except ValueError:
-                ts = -1.0  # unparsed time stamp: the sample still counts for the whole window
+                ts = -1.0
             try:
                 rows.append((ts, float(parts[1]), float(parts[2]), [nm for nm, v in zip(names, parts[3:7]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
         os.unlink(self.f.name)
-        window = "warm-up + timed region + end-to-end loop"
+        window = "whole loaded window (warm-up + timed regions)"
         if timed is not None:
             inside = [r for r in rows if timed[0] <= r[0] <= timed[1]]
             if inside:
-                rows, window = inside, "timed region"
-            elif probe is not None:
-                inside = [r for r in rows if probe[0] <= r[0] <= probe[1]]
-                if inside:
-                    rows, window = inside, "untimed repeat of the same update loop for 0.6 s (the timed region is shorter than nvidia-smi's 100 ms period)"
+                rows, window = inside, "timed regions"
         sm = sorted(r[1] for r in rows)
         mx = rows[-1][2] if rows else None
         reasons = {nm for r in rows for nm in r[3]}
@@ -187,218 +256,175 @@ def measured_peaks():
         return 6650.0, 1590.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 
-def gemm_roofline(lib, torch, S, A, groups=1):
-    """Time the largest grouped launch of the TD7 critic chain (csrc/agent_td7.cuh table C[7]: five
-    independent layers, K up to 768) standalone with CUDA events."""
-    from sac_td3_td7_b200 import _lib
-
-    B, H, Z = BATCH, 256, 256
-    dev = torch.device("cuda")
-    mk = lambda *s: torch.randn(*s, device=dev) * 0.05  # noqa: E731
-    probs, flops, keep = [], 0.0, []
-
-    def add(xs, n_out):
-        nonlocal flops
-        K = sum(x.shape[1] for x in xs)
-        ld = (K + 3) // 4 * 4
-        W, b, y = mk(n_out, ld), mk(n_out), torch.empty(B, n_out, device=dev)
-        keep.extend([W, b, y, *xs])
-        p = _lib.GemmProblem()
-        p.I, p.J, p.C, p.c_ld, p.act, p.bias = B, n_out, y.data_ptr(), n_out, 2, b.data_ptr()
-        off = 0
-        for x in xs:
-            s = p.seg[p.nseg]
-            s.A, s.a_ld, s.B, s.b_ld, s.len = x.data_ptr(), x.shape[1], W.data_ptr() + 4 * off, ld, x.shape[1]
-            p.nseg += 1
-            off += x.shape[1]
-        probs.append(p)
-        flops += 2.0 * B * n_out * K
-
-    zs, a, s2, qn, zsa = mk(B, Z), mk(B, A), mk(B, S), mk(B, H), mk(B, Z)
-    add([zs, a], H)            # fixed_encoder_target.zsa1
-    add([s2, a], H)            # target_q1.q01
-    add([s2, a], H)            # target_q2.q01
-    add([qn, zsa, zs], H)      # q1.q1
-    add([qn, zsa, zs], H)      # q2.q1
-    arr = (_lib.GemmProblem * len(probs))(*probs)
-    ms = C.c_float()
-    _lib.check(lib.b200rl_op_gemm_timed(0, arr, len(probs), groups, int(os.environ.get("B200_GEMM_WARMUP", "20")), int(os.environ.get("B200_GEMM_ITERS", "200")), C.byref(ms), torch.cuda.current_stream().cuda_stream))
-    return flops, ms.value
-
-
-def run_gpu_arm(args):
-    import numpy as np
+def make_agent_and_buffer(workload: str, rank: int):
     import torch
-    import torch.distributed as dist
 
-    from sac_td3_td7_b200 import _lib, build
     from sac_td3_td7_b200.rl.agent import SAC, TD3, TD7
     from sac_td3_td7_b200.rl.replay_memory import LAPReplayMemory, SimpleReplayMemory
 
-    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the update path has no CPU fallback)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    if rank == 0:
-        build.build()
-    if world > 1:
-        dist.barrier()
-    lib = _lib.lib()
-
-    algo, env, prio, seeds, rows = WORKLOADS[args.workload]
-    S, A = ENV_DIMS[env]
-    K, W = args.steps, max(args.warmup, 3)
+    algo, env, prio, seeds, rows, share = WORKLOADS[workload]
     torch.manual_seed(1000 + rank)
     cls = {"TD7": TD7, "TD3": TD3, "SAC": SAC}[algo]
     agent = cls(env, use_lap=prio, n_seeds=seeds) if algo != "SAC" else cls(env, n_seeds=seeds)
-    buf = (LAPReplayMemory if prio else SimpleReplayMemory)(rows, env, n_seeds=seeds, share_rows=seeds > 1)
+    if seeds > 1:
+        agent.seed_population(1000 * (rank + 1))
+    buf = (LAPReplayMemory if prio else SimpleReplayMemory)(rows, env, n_seeds=seeds, share_rows=share)
     buf.fill_synthetic(rows, seed=rank)
-    stream = torch.cuda.current_stream()
+    return agent, buf
 
-    # ---- device-resident throughput: K updates through the burst API ----
-    clocks = ClockSampler(local) if rank == 0 else None
+
+def timed_burst(agent, buf, K, W, dist=None):
+    """K updates through train_ops_n, CUDA events on the launching stream, barrier + synchronize on both sides."""
+    import torch
+
+    stream = torch.cuda.current_stream()
     agent.train_ops_n(W, buf)
     torch.cuda.synchronize()
-    if world > 1:
+    if dist is not None:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
-    wall0 = time.time()
+    w0 = time.time()
     e0.record(stream)
     infos = agent.train_ops_n(K, buf)
     e1.record(stream)
     torch.cuda.synchronize()
-    wall1 = time.time()
+    w1 = time.time()
     ms = e0.elapsed_time(e1)
-    last = {k: (None if v is None else float(v)) for k, v in infos[-1].items()}
-    t = torch.tensor([ms], device="cuda")
-    if world > 1:
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.barrier()
-    ms_max = float(t.item())
-    value = world * seeds * K / (ms_max / 1e3)
+        ms = float(t.item())
+    return ms, infos, (w0, w1)
 
-    # ---- end to end through the drop-in API with host data in the loop ----
-    e2e_steps = min(K, 2000)
+
+def e2e_loop(agent, buf, steps, W, world, total_seeds, dist=None):
+    """The reference-facing per-step API with host data in the loop (rl/runner/run.py:160-171 per environment step)."""
+    import numpy as np
+    import torch
+
+    from sac_td3_td7_b200.population import gather_per_seed
+
+    G, S, A = agent.n_seeds, agent.state_dim, agent.action_dim
     g = np.random.default_rng(5)
-    pinned = torch.empty((64, buf.row_stride), dtype=torch.float32).pin_memory()
-    pinned.copy_(torch.from_numpy(buf.pack(g.standard_normal((64, S), dtype=np.float32), g.random((64, A), dtype=np.float32) * 2 - 1,
-                                           g.standard_normal((64, 1), dtype=np.float32), g.standard_normal((64, S), dtype=np.float32),
-                                           np.ones((64, 1), np.float32))))
-    pinned_np = pinned.numpy()
+    obs = g.standard_normal((64, G, S), dtype=np.float32)
+    act = ((g.random((64, G, A), dtype=np.float32) * 2 - 1) * np.asarray(agent.action_scale, np.float32)).astype(np.float32)  # environment units
+    rew = g.standard_normal((64, G), dtype=np.float32)
+    nxt = g.standard_normal((64, G, S), dtype=np.float32)
+    nd = np.ones((64, G), np.float32)
+    col = agent.INFO_KEYS.index("train/q_fn")
+    gathered = None
 
-    def e2e_step(i):
-        for s in range(seeds if not buf.share_rows else 1):
-            buf.append_rows(pinned_np[i % 64:i % 64 + 1], s)            # H2D of one transition from pinned memory
-        batch = buf.sample(BATCH)
-        info = agent.train_ops(batch, replay_buffer=buf)
-        return float(info["train/q_fn"])                                   # D2H of the info row + sync
+    def step(i):
+        nonlocal gathered
+        j = i % 64
+        if G == 1:
+            buf.append([obs[j, 0], act[j, 0], rew[j, 0], nxt[j, 0], nd[j, 0]])  # one transition: pinned staging slot, read by the append kernel
+            info = agent.train_ops(buf.sample(BATCH), replay_buffer=buf)
+            q = float(info["train/q_fn"])  # D2H: the loss mailbox of this update
+            if dist is not None and i % 10 == 9:
+                gathered = gather_per_seed(torch.tensor([q], device="cuda"), total_seeds)
+            return q
+        buf.append_population(obs[j], act[j], rew[j], nxt[j], nd[j])  # one transition per seed, one launch
+        agent.train_ops(buf.sample(BATCH), replay_buffer=buf)
+        q = agent.read_infos(agent._n_calls, 1, -1)[:, 0, col]  # every seed's loss: one strided D2H + sync
+        if dist is not None and i % 10 == 9:  # metrics all-gather over NCCL / NVLink (eval returns in a real run)
+            gathered = gather_per_seed(torch.from_numpy(q).cuda(), total_seeds)
+        return q
 
-    e2e = None
-    if seeds == 1:
-        for i in range(W):
-            e2e_step(i)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            e2e_step(i)
-        torch.cuda.synchronize()
-        el = time.perf_counter() - t0
+    for i in range(W):
+        step(i)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(i)
+    torch.cuda.synchronize()
+    el = time.perf_counter() - t0
+    if dist is not None:
         t = torch.tensor([el], device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * e2e_steps / float(t.item()), "unit": "updates/s", "h2d_bytes_per_step": buf.row_stride * 4,
-               "d2h_bytes_per_step": 8 * len(agent.INFO_KEYS), "steps": e2e_steps,
-               "note": "per step: append 1 transition from pinned host memory, sample(256), train_ops, float(info['train/q_fn']) -- the engine posts "
-                       "every loss of the step to a pinned host mailbox the moment its kernel has run (8 B per value), so the read returns while "
-                       "the step's backward pass is still executing and the next step's host calls overlap it; full sync at the end of the loop"}
-    probe = None
-    if wall1 - wall0 < 0.35:  # too short for nvidia-smi's 100 ms period: sample the same loop, untimed, for 0.6 s more
-        p0 = time.time()
-        while time.time() - p0 < 0.6:
-            agent.train_ops_n(max(1, min(K, 200)), buf)
-            torch.cuda.synchronize()
-        probe = (p0, time.time())
-    clk = clocks.stop(timed=(wall0, wall1), probe=probe) if clocks else None
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        el = float(t.item())
+    cols = len(agent.INFO_KEYS)
+    rs = buf.row_stride
+    return {"value": world * G * steps / el, "unit": "updates/s", "h2d_bytes_per_step": (1 if buf.share_rows else G) * rs * 4, "d2h_bytes_per_step": G * cols * 4 if G > 1 else 8,
+            "steps": steps, "seconds": el, "gathered_seeds": None if gathered is None else int(gathered.shape[0]),
+            "note": ("per step: one transition per seed appended from the library's pinned staging ring (read over the bus by the append kernel), sample(256) "
+                     "straight into the engine's input buffers, train_ops, every seed's train/q_fn read back; every 10th step an NCCL all-gather of the per-seed "
+                     "metric across ranks" if G > 1 else
+                     "per step: append 1 transition from pinned host memory, sample(256), train_ops, float(info['train/q_fn']) from the pinned loss mailbox")}
 
-    # ---- rooflines (rank 0, standalone event-timed launches) ----
-    hbm_peak, bf16_burst, bf16_sus, peak_src = measured_peaks()
-    g_flops, g_ms = gemm_roofline(lib, torch, S, A)
-    ach_tf = g_flops / (g_ms * 1e-3) / 1e12
-    roofline = {"kernel": "gemm_kernel<fwd> (grouped FFMA GEMM, 5 independent layers of the TD7 critic chain, 320 CTAs)", "bound": "tensor",
-                "achieved": ach_tf, "peak": bf16_burst, "unit": "TFLOP/s", "frac": ach_tf / bf16_burst,
-                "traffic": 2.7392e6,  # dram__bytes_read + write of this launch, profiles/gemm_ffma_ncu_full_r01.summary.txt (operands are L2-resident)
-                "peak_source": peak_src + ", dense bf16 cuBLAS burst",
-                "note": "fp32 FFMA by design (1e-5 fp32 parity rules out single-pass TF32/BF16); the non-tensor fp32 peak of a B200 is ~74.5 TFLOP/s",
-                "fp32_ffma_peak_tflops": 74.5, "frac_of_fp32_ffma_peak": ach_tf / 74.5, "launch_ms": g_ms, "flops_per_launch": g_flops}
-    roof2 = None
-    if prio:
-        ms2 = (C.c_float * 2)()
-        _lib.check(lib.b200rl_replay_time_sample(buf._h, BATCH, 10, 200, ms2, stream.cuda_stream))
-        bytes_scan = 4.0 * rows * seeds
-        row_bytes = 4.0 * (2 * S + A + 2)
-        nsuper = -(-rows // (256 * 64))
-        # per draw: the super sums, 64 tile sums, 256 priorities, the packed row in and the five batch tensors out, the index
-        bytes_walk = seeds * BATCH * (nsuper * 8 + 64 * 8 + 256 * 4 + row_bytes * 2 + 8 + 4)
-        # dram__bytes_read + write of one launch from the committed ncu --set full captures (profiles/lap_sample_*_ncu_full_r01.summary.txt)
-        ncu_traffic = {"td7_halfcheetah_1M": 0.379e6, "td7_humanoid_pop256": 422.8e6, "td7_ant_pop256": 95.8e6}.get(args.workload)
-        roof2 = {"kernel": "lap_sample_kernel (per draw: walk of the 3-level fp64 sum tree + row gather; the only replay kernel on the per-step path)",
-                 "bound": "hbm", "achieved": bytes_walk / (ms2[1] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                 "frac": bytes_walk / (ms2[1] * 1e-3) / 1e9 / hbm_peak, "traffic": ncu_traffic, "launch_ms": ms2[1], "bytes_per_launch": bytes_walk, "peak_source": peak_src,
-                 "note": "latency-bound by construction for one agent (256 warps, three dependent L2 round trips each); the tree itself is repaired in place by the "
-                         "kernels that write priorities, so no per-step pass over the 4 MB priority array remains.  Stacked seeds (256 x 256 draws per launch): "
-                         "HBM-bound on Humanoid rows (ncu: 423 MB of DRAM traffic in 87 us = 59 % of ncu's DRAM peak, 74 % of the measured copy peak), "
-                         "issue-bound on Ant rows (663 instructions per draw, issue slots 74 % busy)",
-                 "full_rebuild_kernel": {"kernel": "lap_tile_sums_kernel (bulk loads / restored checkpoints only)", "launch_ms": ms2[0], "bytes_per_launch": bytes_scan,
-                                         "achieved_gbs": bytes_scan / (ms2[0] * 1e-3) / 1e9}}
 
-    roof3 = None
-    if seeds >= 8:  # stacked seeds: the tcgen05 kernels (HBM- and tensor-side figures, SURVEY 8d)
-        roof3 = {}
-        for mode, name in ((0, "forward"), (2, "wgrad_adam")):
-            fl, by, ms3 = stacked_roofline(lib, torch, seeds, mode)
-            roof3[name] = {"kernel": "gemm_tc_ws_kernel (persistent tcgen05 TF32, TMA-fed), 2 layers x %d seeds" % seeds, "launch_ms": ms3,
-                           "hbm": {"achieved": by / (ms3 * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": by / (ms3 * 1e-3) / 1e9 / hbm_peak},
-                           "tensor": {"achieved": fl / (ms3 * 1e-3) / 1e12, "peak": bf16_sus, "unit": "TFLOP/s", "frac": fl / (ms3 * 1e-3) / 1e12 / bf16_sus,
-                                      "note": "TF32 issue rate is half of bf16; the stacked update is HBM-bound at B=256 per seed"},
-                           "bytes_per_launch": by, "flops_per_launch": fl, "peak_source": peak_src}
+def act_append_latency(agent, buf):
+    """Host-to-host latency of agent.sample(obs) and of replay.append(transition), microseconds."""
+    import numpy as np
+    import torch
 
-    # ---- CPU baseline (oracle port) on this host, bounded ----
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        ups, n, el, threads = cpu_updates_per_s(args.workload if seeds == 1 else "td7_ant_1M", budget_s=15.0)
-        cpu = {"value": ups, "unit": "updates/s", "cores": threads, "kind": "port",
-               "sample": f"{n} updates of the oracle port of the reference CPU loop ({threads} torch threads, os.cpu_count={os.cpu_count()}) in {el:.1f}s, same workload"}
+    G, S, A = agent.n_seeds, agent.state_dim, agent.action_dim
+    g = np.random.default_rng(1)
+    obs = g.standard_normal((G, S)).astype(np.float32)
+    o = obs if G > 1 else obs[0]
+    torch.cuda.synchronize()
+    for _ in range(20):
+        agent.sample(o, True)
+    t0 = time.perf_counter()
+    n = 300
+    for _ in range(n):
+        agent.sample(o, True)
+    act_us = (time.perf_counter() - t0) / n * 1e6
+    a = (g.random((G, A), dtype=np.float32) * 2 - 1) * np.asarray(agent.action_scale, np.float32)
+    r, nd = np.zeros(G, np.float32), np.ones(G, np.float32)
+    ap = (lambda: buf.append([obs[0], a[0], 0.0, obs[0], 1.0])) if G == 1 else (lambda: buf.append_population(obs, a, r, obs, nd))
+    for _ in range(20):
+        ap()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        ap()
+    host_us = (time.perf_counter() - t0) / n * 1e6
+    torch.cuda.synchronize()
+    total_us = (time.perf_counter() - t0) / n * 1e6
+    return {"act_us": act_us, "append_host_us": host_us, "append_us": total_us,
+            "note": "act_us: agent.sample(obs, deterministic) host to host (pinned observation slot -> one cluster kernel per seed -> pinned action mailbox, no stream "
+                    "sync); append_host_us: host time of replay.append per call (asynchronous); append_us: the same including the device work (synchronised at the end)"}
 
+
+def single_agent_record(workload: str, K: int, with_cpu: bool, lib):
+    import torch
+
+    algo, env, prio, seeds, rows, share = WORKLOADS[workload]
+    S, A = ENV_DIMS[env]
+    agent, buf = make_agent_and_buffer(workload, 0)
+    K = max(K, MIN_SINGLE_UPDATES) if seeds == 1 else max(K, 20)
+    ms, infos, _ = timed_burst(agent, buf, K, 20 if seeds == 1 else 3)
+    value = seeds * K / (ms / 1e3)
+    e2e = e2e_loop(agent, buf, min(K, 2000) if seeds == 1 else min(K, 50), 5, 1, seeds)
+    lat = act_append_latency(agent, buf)
     lp0, lp1 = lib.b200rl_agent_launches_per_update(agent._h, 0), lib.b200rl_agent_launches_per_update(agent._h, 1)
-    per_update = (lp0 + lp1) / 2.0 if algo != "SAC" else float(lp1)
-    gflop = algorithmic_gflop(algo, S, A)
-    line = {
-        "metric": "gradient updates/sec (batch 256) per agent" if seeds == 1 else "agent-updates/sec (batch 256)",
-        "value": value, "unit": "updates/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "algo": algo, "env": env, "obs_dim": S, "act_dim": A, "batch": BATCH, "buffer_rows": rows,
-                   "replay": "LAP" if prio else "uniform", "seeds_per_gpu": seeds, "parallelism": f"replicas x{world} (independent agents, no data-path collective)",
-                   "l2": "replay rows exceed L2 (1M rows); weights, Adam moments and the 4 MB priority array are L2-resident by design -- they are the loop state"},
-        "e2e": e2e, "gpu_launches": int(K * (per_update + 1)), "launches_per_update": {"critic_only": lp0, "with_actor": lp1},
-        "clocks": clk, "roofline": roofline, "roofline_replay": roof2, "roofline_stacked": roof3, "cpu_baseline": cpu,
-        "algorithmic_gflop_per_update": gflop, "update_tflops_per_gpu": gflop * value / 1e3 / world,
-        "last_info": last,
-    }
-    if cpu:
-        line["speedup_vs_cpu_port"] = {"device_resident": value / cpu["value"], "e2e": (e2e["value"] / cpu["value"]) if e2e else None}
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    rec = {"workload": workload, "config": workload_config(workload, 1), "value": value, "unit": "updates/s", "us_per_update": 1e3 * ms / K if seeds == 1 else None,
+           "ms_per_stacked_update": ms / K if seeds > 1 else None, "timed_updates": K, "e2e": e2e, **lat,
+           "launches_per_update": {"critic_only": lp0, "with_actor": lp1}, "algorithmic_gflop_per_update": algorithmic_gflop(algo, S, A),
+           "last_info": {k: (None if v is None else float(v)) for k, v in infos[-1].items()}}
+    if seeds > 1:
+        rec["roofline_whole_update"] = whole_update_roofline(value, S, A)
+    del agent, buf
+    torch.cuda.empty_cache()
+    if with_cpu:
+        cpu = cpu_updates_per_s(workload if seeds == 1 else workload.replace("pop256", "1M"), budget_s=24.0)
+        rec["cpu_baseline"] = cpu
+        rec["speedup_vs_cpu"] = {"device_resident": value / cpu["value"], "e2e": e2e["value"] / cpu["value"],
+                                 "against": f"the better of the CPU arm's thread settings ({cpu['cores']} threads, kind {cpu['kind']})"}
+    return rec
+
+
+def whole_update_roofline(agent_updates_per_s_per_gpu: float, S: int, A: int):
+    hbm_peak, _, _, src = measured_peaks()
+    mb = algorithmic_mbytes_stacked(S, A)
+    ach = mb * 1e6 * agent_updates_per_s_per_gpu / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "algorithmic_mbytes_per_seed_update": mb, "peak_source": src,
+            "note": "SURVEY 8(d) algorithmic bytes of one TD7 seed-update (weights + Adam state of the trained nets, frozen nets once) x agent-updates/s per GPU"}
 
 
 def stacked_roofline(lib, torch, G, mode):
@@ -406,7 +432,6 @@ def stacked_roofline(lib, torch, G, mode):
     bias + ELU; mode 2: weight gradient + fused Adam).  Returns (flops, algorithmic bytes, ms per launch)."""
     from sac_td3_td7_b200 import _lib
 
-    os.environ.setdefault("B200RL_TC", "1")
     dev = torch.device("cuda")
     Bn, H, K = 256, 256, 256
     keep, probs = [], []
@@ -439,18 +464,129 @@ def stacked_roofline(lib, torch, G, mode):
     return flops, byts, ms.value
 
 
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from sac_td3_td7_b200 import _lib, build
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the update path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    D = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        D = dist
+    if rank == 0:
+        build.build()
+    if D:
+        D.barrier()
+    lib = _lib.lib()
+
+    algo, env, prio, seeds, rows, share = WORKLOADS[args.workload]
+    S, A = ENV_DIMS[env]
+    K, W = args.steps, max(args.warmup, 3)
+    if seeds == 1 and not args.steps_given:
+        K = MIN_SINGLE_UPDATES
+    agent, buf = make_agent_and_buffer(args.workload, rank)
+
+    clocks = ClockSampler(local) if rank == 0 else None
+    ms_max, infos, (w0, w1) = timed_burst(agent, buf, K, W, D)
+    value = world * seeds * K / (ms_max / 1e3)
+    last = {k: (None if v is None else float(v)) for k, v in infos[-1].items()}
+    e2e_steps = min(K, 2000) if seeds == 1 else min(K, 100)
+    e2e = e2e_loop(agent, buf, e2e_steps, W, world, seeds * world, D)
+    w2 = time.time()
+    clk = clocks.stop(timed=(w0, w2)) if clocks else None
+    lat = act_append_latency(agent, buf) if rank == 0 else None
+    lp0, lp1 = lib.b200rl_agent_launches_per_update(agent._h, 0), lib.b200rl_agent_launches_per_update(agent._h, 1)
+    if rank != 0:
+        if D:
+            D.barrier()
+            D.destroy_process_group()
+        return
+
+    # ---- rooflines (rank 0, standalone graph-timed launches) ----
+    hbm_peak, bf16_burst, bf16_sus, peak_src = measured_peaks()
+    roofline, roof_extra = None, {}
+    if seeds >= 8:
+        # dominant kernel of the stacked update (30 % of its kernel time, profiles/): persistent tcgen05 weight gradient + fused Adam
+        fl, by, ms3 = stacked_roofline(lib, torch, seeds, 2)
+        ach = by / (ms3 * 1e-3) / 1e9
+        roofline = {"kernel": f"gemm_tc_ws_kernel<wgrad> (persistent tcgen05 TF32, TMA-fed, fused Adam), 2 layers x {seeds} seeds", "bound": "hbm", "achieved": ach,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": 1001.2e6, "launch_ms": ms3, "bytes_per_launch": by,
+                    "peak_source": peak_src + " (burst: kernel timed alone)",
+                    "note": "algorithmic bytes per launch = 2 layers x seeds x 4 B x (dZ 256x256 + X 256x256 + p, m, v in and out 6 x 256x256), SURVEY 8(d) 24 B/param; "
+                            "traffic = dram__bytes_read + write of the same launch, profiles/gemm_tc_ws_mode2_ncu_full_r01.summary.txt",
+                    "tensor": {"achieved": fl / (ms3 * 1e-3) / 1e12, "peak": bf16_sus, "unit": "TFLOP/s", "frac": fl / (ms3 * 1e-3) / 1e12 / bf16_sus}}
+        fl0, by0, ms0 = stacked_roofline(lib, torch, seeds, 0)
+        roof_extra["roofline_forward"] = {"kernel": "gemm_tc_ws_kernel<fwd>, 2 layers x %d seeds" % seeds, "bound": "hbm", "achieved": by0 / (ms0 * 1e-3) / 1e9, "peak": hbm_peak,
+                                          "unit": "GB/s", "frac": by0 / (ms0 * 1e-3) / 1e9 / hbm_peak, "launch_ms": ms0, "bytes_per_launch": by0,
+                                          "tensor": {"achieved": fl0 / (ms0 * 1e-3) / 1e12, "peak": bf16_sus, "unit": "TFLOP/s", "frac": fl0 / (ms0 * 1e-3) / 1e12 / bf16_sus}}
+        roof_extra["roofline_whole_update"] = whole_update_roofline(value / world, S, A)
+    roof2 = None
+    if prio:
+        ms2 = (C.c_float * 2)()
+        _lib.check(lib.b200rl_replay_time_sample(buf._h, BATCH, 10, 100, ms2, torch.cuda.current_stream().cuda_stream))
+        gather_bytes = seeds * BATCH * 2.0 * 4.0 * (2 * S + A + 2)  # rows read + batch tensors written
+        roof2 = {"kernel": "lap_sample_kernel (3-level fp64 sum-tree walk + row gather, one warp per draw)", "bound": "hbm", "achieved": gather_bytes / (ms2[1] * 1e-3) / 1e9,
+                 "peak": hbm_peak, "unit": "GB/s", "frac": gather_bytes / (ms2[1] * 1e-3) / 1e9 / hbm_peak, "launch_ms": ms2[1], "bytes_per_launch": gather_bytes,
+                 "peak_source": peak_src,
+                 "note": "algorithmic bytes = seeds x B x 2 x 4(2S+A+2) (SURVEY 8(d) gather term; the tree levels a draw reads are L2-resident and not counted)",
+                 "full_rebuild_kernel": {"kernel": "lap_tile_sums_kernel (bulk loads / restored checkpoints only)", "launch_ms": ms2[0], "bytes_per_launch": 4.0 * rows * seeds,
+                                         "achieved_gbs": 4.0 * rows * seeds / (ms2[0] * 1e-3) / 1e9}}
+
+    # ---- CPU baseline on this host (rank 0, N = 1), and the single-agent sub-records ----
+    cpu, singles = None, None
+    del agent, buf
+    torch.cuda.empty_cache()
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_updates_per_s(args.workload if seeds == 1 else args.workload.replace("pop256", "1M"), budget_s=24.0)
+    if world == 1 and args.workload == DEFAULT_WORKLOAD and not args.no_sub_records:
+        singles = {}
+        for name in ("td7_humanoid_1M", "td7_halfcheetah_1M", "sac_walker2d_1M", "td7_humanoid_pop256"):
+            singles[name] = single_agent_record(name, K, with_cpu=(name in ("td7_humanoid_1M",) and not args.no_cpu_baseline), lib=lib)
+
+    per_update = (lp0 + lp1) / 2.0 if algo != "SAC" else float(lp1)
+    gflop = algorithmic_gflop(algo, S, A)
+    line = {
+        "metric": METRIC, "value": value, "unit": "updates/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (stacked seeds: TF32 tensor-core inputs, fp32 accumulate and state)" if seeds >= 8 else "f32",
+        "data": "synthetic", "config": workload_config(args.workload, world),
+        "e2e": e2e, "gpu_launches": int(K * (per_update + 1)), "launches_per_update": {"critic_only": lp0, "with_actor": lp1},
+        "clocks": clk, "roofline": roofline, "roofline_replay": roof2, **roof_extra, "cpu_baseline": cpu, **(lat or {}),
+        "algorithmic_gflop_per_update": gflop, "update_tflops_per_gpu": gflop * value / 1e3 / world,
+        "single_agent": singles, "last_info": last,
+    }
+    if roofline is None:  # single-agent workloads: the launch-bound update has no bandwidth / tensor roofline; report the FFMA fraction
+        line["roofline"] = {"kernel": "whole update (persistent fp32 FFMA dataflow kernels)", "bound": "tensor", "achieved": gflop * value / 1e3 / world, "peak": bf16_burst,
+                            "unit": "TFLOP/s", "frac": gflop * value / 1e3 / world / bf16_burst, "traffic": None, "peak_source": peak_src,
+                            "note": "fp32 FFMA by design (1e-5 fp32 parity); the non-tensor fp32 peak of a B200 is ~74.5 TFLOP/s",
+                            "frac_of_fp32_ffma_peak": gflop * value / 1e3 / world / 74.5}
+    if cpu:
+        line["speedup_vs_cpu"] = {"device_resident": value / cpu["value"], "e2e": e2e["value"] / cpu["value"],
+                                  "against": f"one agent on the host CPU, better of the thread settings ({cpu['cores']} threads, kind {cpu['kind']})"}
+    print(json.dumps(line), flush=True)
+    if D:
+        D.barrier()
+        D.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub-records", action="store_true")
     args = ap.parse_args()
     args.steps_given = args.steps is not None
     if args.steps is None:
-        args.steps = 2000
+        args.steps = 50
     if args.impl == "reference":
         run_reference_arm(args)
     else:

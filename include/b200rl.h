@@ -41,6 +41,12 @@ int b200rl_is_cuda_build(void);
  * measurements and the parity tests of both paths. */
 int b200rl_set_mma(int on);
 
+/* Update engine of single agents created AFTERWARDS: 0 = one CUDA-graph node per grouped layer launch (default), 1 = the
+ * persistent dataflow kernels of csrc/mega.cuh (a whole phase of the update as one launch, tiles ordered by counters in
+ * global memory; parity-green, slower on B200 -- an experiment kept for A/B), -1 = default / B200RL_MEGA.  Returns the
+ * previous override. */
+int b200rl_set_mega(int on);
+
 /* ---- raw device memory helpers (tests, benches; Python normally uses torch tensors) ---- */
 int b200rl_malloc(void** out_dev, uint64_t bytes);
 int b200rl_free(void* dev);

@@ -69,6 +69,7 @@ SIGNATURES = {
     "b200rl_version": (C.c_int, []),
     "b200rl_is_cuda_build": (C.c_int, []),
     "b200rl_set_mma": (C.c_int, [C.c_int]),
+    "b200rl_set_mega": (C.c_int, [C.c_int]),
     "b200rl_malloc": (C.c_int, [C.POINTER(c_vp), C.c_uint64]),
     "b200rl_free": (C.c_int, [c_vp]),
     "b200rl_memcpy_h2d": (C.c_int, [c_vp, c_vp, C.c_uint64, c_vp]),

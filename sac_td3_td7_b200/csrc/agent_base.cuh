@@ -3,6 +3,7 @@
 #pragma once
 #include "nets.cuh"
 #include "replay.cuh"
+#include "mega.cuh"
 
 namespace b200rl {
 
@@ -148,6 +149,38 @@ struct AgentBase {
     B200_CHECK_CUDA(cudaMemcpyAsync(dst.p, src.p, (size_t)G * src.L.numel * sizeof(float), cudaMemcpyDeviceToDevice, s));
     return kOk;
   }
+
+#ifndef B200_EMU
+  // the persistent dataflow path (mega.cuh): an option (B200RL_MEGA=1 / b200rl_set_mega), single agents only (stacked
+  // seeds share the step counters, which the per-seed counters of the dataflow kernel do not order).  It is parity-green
+  // but NOT the default: measured on B200 a TD7 update takes 382 us through it against 205 us through the
+  // launch-per-layer graphs -- the 32 x 32 FFMA tile sustains ~28 tiles/us machine-wide either way (20 % of the fp32
+  // peak, shared-memory fragment traffic), the classic graphs already keep the machine that busy with 2.4 launches in
+  // flight, and the dataflow kernel adds ~3 us of ticket / descriptor / counter traffic per tile (profiles/README.md).
+  static int& mega_override() { static int v = -1; return v; }
+  bool use_mega() const {
+    static const bool on = [] { const char* e = getenv("B200RL_MEGA"); return e ? atoi(e) != 0 : false; }();
+    return (mega_override() >= 0 ? mega_override() != 0 : on) && G == 1;
+  }
+  PrepArgs prep_args(unsigned step_mask) const {
+    PrepArgs p;
+    memset(&p, 0, sizeof(p));
+    p.st = d_step; p.adam = d_adam; p.hyper = d_hyper; p.nopt = nopt; p.step_mask = step_mask; p.ring = kInfoRing;
+    return p;
+  }
+  GaussArgs gauss_args(const Mat& noise, int stream_id) const {
+    GaussArgs ga;
+    memset(&ga, 0, sizeof(ga));
+    ga.out_base = noise.p; ga.gs = noise.gs; ga.n = (long long)noise.rows * noise.cols; ga.seed0 = rng_seed;
+    ga.step_counter = &d_step->n_runs; ga.inject = d_flags; ga.stream_id = stream_id;
+    return ga;
+  }
+  static int sm_count() {
+    static const int n = [] { int v = 148, d = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
+    return n;
+  }
+#endif
+  virtual int rebuild_mega() { return kOk; }  // (re)record the dataflow programs: at build time and when a baked scalar (the RNG seed) changes
 
   int launch_prep(unsigned step_mask, cudaStream_t s) {
     B200_LAUNCH(prep_step_kernel, dim3(1), dim3(32), 0, s, d_step, d_adam, d_hyper, nopt, step_mask, kInfoRing);

@@ -250,9 +250,94 @@ struct TD7Agent : AgentBase {
       B200_TRY(up(Wp[3], kWgrad, w0));
     }
     built = true;
+    B200_TRY(rebuild_mega());
     return kOk;
   }
   RowTable critic_norm_bwd;
+
+#ifndef B200_EMU
+  // ---- the update as three persistent dataflow launches (mega.cuh): [A] everything forward, [B] encoder / critic
+  // backward with the weight gradients (+ Adam) and, on actor steps, the critics' forward at pi(s), [C] the actor's
+  // backward.  Only the loss kernels (and the LAP write-back beside [B]) remain separate launches.
+  std::unique_ptr<MegaProgram> MA[2], MB[2], MC;
+  int rebuild_mega() override {
+    if (!use_mega()) return kOk;
+    for (int v = 0; v < 2; ++v) {
+      const bool actor = v == 1;
+      auto a = std::make_unique<MegaProgram>();
+      a->add_prep(prep_args(actor ? 0x7u : 0x6u));
+      a->add_gauss(gauss_args(noise, 0));
+      for (int i : {0, 1, 2}) a->add_gemm_table(E[i]);
+      a->add_row_ops(En[0].h_ops, false);
+      for (int i : {3, 4, 5}) a->add_gemm_table(E[i]);
+      a->add_gemm_table(C[0]);
+      a->add_row_ops(CnQ.h_ops, false);
+      a->add_gemm_table(C2v[v]);
+      a->add_row_ops(CnP[v].h_ops, false);
+      a->add_gemm_table(C[3]);
+      a->add_row_ops(Cn[2].h_ops, false);
+      if (actor) for (int i = 0; i <= 5; ++i) a->add_gemm_table(Aa[i]);
+      for (int i : {4, 5, 6, 7}) a->add_gemm_table(C[i]);
+      a->add_row_ops(Cn[3].h_ops, false);
+      for (int i : {8, 9, 10, 11, 12}) a->add_gemm_table(C[i]);
+      B200_TRY(a->build(&arena, G, sm_count()));
+      MA[v] = std::move(a);
+
+      auto b = std::make_unique<MegaProgram>();
+      b->add_gemm_table(C[13]); b->add_gemm_table(Wq[0]);
+      b->add_gemm_table(C[14]); b->add_gemm_table(Wq[1]);
+      b->add_gemm_table(C[15]); b->add_gemm_table(Wq[2]);
+      b->add_row_ops(critic_norm_bwd.h_ops, true);
+      b->add_gemm_table(Wq[3]);
+      b->add_gemm_table(E[6]); b->add_gemm_table(We[5]);
+      b->add_gemm_table(E[7]); b->add_gemm_table(We[4]);
+      b->add_gemm_table(E[8]); b->add_gemm_table(We[3]);
+      b->add_row_ops(En[1].h_ops, true);
+      b->add_gemm_table(E[9]); b->add_gemm_table(We[2]);
+      b->add_gemm_table(E[10]); b->add_gemm_table(We[1]); b->add_gemm_table(We[0]);
+      if (actor) {
+        b->add_gemm_table(Aa[6]);
+        b->add_row_ops(An[0].h_ops, false);
+        for (int i : {7, 8, 9}) b->add_gemm_table(Aa[i]);
+      }
+      B200_TRY(b->build(&arena, G, sm_count()));
+      MB[v] = std::move(b);
+    }
+    auto c = std::make_unique<MegaProgram>();
+    for (int i : {10, 11, 12}) c->add_gemm_table(Aa[i]);
+    c->add_row_ops(An[1].h_ops, true);
+    for (int i : {13, 14, 15, 16}) c->add_gemm_table(Aa[i]);
+    c->add_gemm_table(Wp[0]);
+    c->add_gemm_table(Aa[17]); c->add_gemm_table(Wp[1]);
+    c->add_gemm_table(Aa[18]); c->add_gemm_table(Wp[2]);
+    c->add_row_ops(An[2].h_ops, true);
+    c->add_gemm_table(Wp[3]);
+    B200_TRY(c->build(&arena, G, sm_count()));
+    MC = std::move(c);
+    return kOk;
+  }
+  int issue_step_mega(int variant) {
+    const bool actor = (variant & 1) != 0;
+    cudaStream_t M = stream, sE = fork.side[0], sP = fork.side[3];
+    B200_TRY(MA[variant]->launch(M));
+    B200_TRY(fork.link(M, sE));
+    B200_TRY(launch_enc_loss(sE));
+    B200_TRY(launch_critic_loss(M));
+    const bool fix_tree = use_lap && bound != nullptr;  // LAP write-back + sum-tree repair beside the backward pass
+    if (fix_tree) {
+      B200_TRY(fork.link(M, sP));
+      B200_TRY(bound->scatter_and_fix(prio_dbg.p, act_stride, B, sP));
+    }
+    B200_TRY(fork.link(sE, M));
+    B200_TRY(MB[variant]->launch(M));
+    if (actor) {
+      B200_TRY(launch_actor_loss(M));
+      B200_TRY(MC->launch(M));
+    }
+    if (fix_tree) B200_TRY(fork.link(sP, M));
+    return kOk;
+  }
+#endif
 
 #define GL(tbl, st) B200_TRY(gemm_table_launch(tbl, G, st))
 #define RL(tbl, st) B200_TRY(row_table_launch(tbl, G, st))
@@ -292,6 +377,9 @@ struct TD7Agent : AgentBase {
 
   // variant: bit0 = actor step
   int issue_step(int variant) override {
+#ifndef B200_EMU
+    if (use_mega() && MC) return issue_step_mega(variant);  // (recorded at creation when the option was on)
+#endif
     const bool actor = (variant & 1) != 0;
     cudaStream_t M = stream, sE = fork.side[0], sA = fork.side[1], sN = fork.side[2], sP = fork.side[3];
     // counters / Adam scalars / smoothing noise: off the critical path, joined where first needed

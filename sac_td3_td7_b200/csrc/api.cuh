@@ -83,6 +83,17 @@ int b200rl_set_mma(int on) {
   return prev;
 }
 
+int b200rl_set_mega(int on) {
+#ifndef B200_EMU
+  const int prev = AgentBase::mega_override();
+  AgentBase::mega_override() = on < 0 ? -1 : (on != 0);
+  return prev;
+#else
+  (void)on;
+  return -1;
+#endif
+}
+
 int b200rl_malloc(void** out_dev, uint64_t bytes) {
   B200_TRY(ensure_device());
   B200_CHECK_CUDA(cudaMalloc(out_dev, bytes ? bytes : 16));
@@ -523,7 +534,7 @@ int b200rl_agent_set_rng(b200rl_agent* h, uint64_t seed) {
   B200_REQUIRE(h, "null argument");
   h->base->rng_seed = seed;
   h->base->drop_graphs();  // the seed is a baked kernel argument
-  return kOk;
+  return h->base->rebuild_mega();
 }
 
 int b200rl_agent_io(b200rl_agent* h, float** ss_dev, float** action_dev, float** reward_dev, float** notdone_dev, int64_t* group_stride) {
@@ -733,6 +744,13 @@ int b200rl_debug_timeline(unsigned long long* out256x2) {
   static unsigned long long init[256][2];
   for (auto& e : init) { e[0] = ~0ull; e[1] = 0ull; }
   return cudaMemcpyToSymbol(g_tl, init, sizeof(init)) == cudaSuccess ? 0 : 1;
+}
+// per-tile trace of the persistent dataflow kernels: out[programs = 8][tiles = 4096][5]; resets the buffer
+int b200rl_debug_mega_trace(unsigned long long* out) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out, g_mega_trace, sizeof(g_mega_trace)) != cudaSuccess) return 1;
+  std::vector<unsigned long long> zero(sizeof(g_mega_trace) / 8, 0ull);
+  return cudaMemcpyToSymbol(g_mega_trace, zero.data(), sizeof(g_mega_trace)) == cudaSuccess ? 0 : 1;
 }
 int b200rl_debug_probe(long long* out64x10) {
   cudaDeviceSynchronize();

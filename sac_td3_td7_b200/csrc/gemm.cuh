@@ -435,7 +435,20 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], 
 #endif
 
 // four consecutive floats of an epilogue operand, all loads in flight at once
+template <bool CG = false>
 __device__ __forceinline__ void load_quad(float (&o)[4], const float* p, int nvalid) {
+#ifndef B200_EMU
+  if (CG) {
+    if (nvalid == 4 && aligned16(p)) {
+      const float4 t = __ldcg(reinterpret_cast<const float4*>(p));
+      o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = (e < nvalid) ? __ldcg(p + e) : 0.f;
+    }
+    return;
+  }
+#endif
   if (nvalid == 4 && aligned16(p)) {
     const float4 t = *reinterpret_cast<const float4*>(p);
     o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
@@ -443,6 +456,19 @@ __device__ __forceinline__ void load_quad(float (&o)[4], const float* p, int nva
 #pragma unroll
     for (int e = 0; e < 4; ++e) o[e] = (e < nvalid) ? p[e] : 0.f;
   }
+}
+template <bool CG>
+__device__ __forceinline__ AdamScalars load_adam(const AdamScalars* p) {
+#ifndef B200_EMU
+  if (CG) {
+    const float4 a = __ldcg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldcg(reinterpret_cast<const float4*>(p) + 1);
+    AdamScalars s;
+    s.w1 = a.x; s.beta2 = a.y; s.w2 = a.z; s.bc2_sqrt = a.w; s.neg_step = b.x; s.eps = b.y; s.step = __float_as_int(b.z); s.pad = 0;
+    return s;
+  }
+#endif
+  return *p;
 }
 __device__ __forceinline__ void store_quad(float* p, const float (&o)[4], int nvalid) {
   if (nvalid == 4 && aligned16(p)) {
@@ -460,34 +486,22 @@ __device__ __forceinline__ void store_quad(float* p, const float (&o)[4], int nv
 // MMA = true: the chunk products run on the tensor cores as 3xTF32 (mma.sync fragments read straight from the same
 // cp.async-staged tiles, with the fragment-friendly swizzles); everything around the product loop -- staging, split-K
 // clusters, the fixed-order cross-warp reduction, the fused epilogues -- is shared with the FFMA variant.
-template <int MODE, bool MMA>
-__global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_constant__ FfmaLaunch L) {
-  B200_PDL_TRIGGER();  // the setup below reads kernel parameters only: it may overlap the previous kernel
+// One output tile of one problem.  `sp` may live in kernel-parameter memory (classic launches) or in shared memory (the
+// persistent dataflow kernel, mega.cuh).  PERSIST = true: no split-K cluster, no programmatic-launch wait, and every
+// operand the epilogue reads goes through L2 (ld.global.cg) -- it may have been written by another SM inside the
+// same kernel, where L1 is not invalidated between tiles.
+template <int MODE, bool MMA, bool PERSIST>
+__device__ __forceinline__ void gemm_tile(const FfmaProblem& sp, int t_local, int g, int split, int splitk_arg, float* smem) {
   B200_PROBE_DECL
-  B200_TIMELINE(L.tag)
   constexpr bool A_KM = (MODE != kWgrad);  // A contiguous along the reduction in global memory
   constexpr bool B_KM = (MODE == kFwd);
-  // 3 pipeline stages x (A tile 32x64, B tile 32x64) = 48 KB; the first 32 KB later hold the 8 partial tiles;
-  // behind them one 4 KB receive slot per non-leader CTA of the split-K cluster
-  B200_DYN_SMEM(float, smem);
-
   const int tid = threadIdx.x;
-  const int g = blockIdx.y;
-  int tile_id = (int)blockIdx.x, split = 0;
 #ifndef B200_EMU
-  const int splitk = L.splitk;
-  if (splitk > 1) {
-    cluster_arrive();  // phase 1: "my shared memory exists" (waited on just before the DSMEM pushes)
-    tile_id = (int)cluster_id_x();
-    split = (int)cluster_ctarank();
-  }
+  const int splitk = PERSIST ? 1 : splitk_arg;
 #else
   constexpr int splitk = 1;
+  (void)splitk_arg;
 #endif
-  int pi = 0;
-  while (pi + 1 < L.nprob && tile_id >= L.p[pi + 1].tile_begin) ++pi;
-  const FfmaProblem& sp = L.p[pi];
-  const int t_local = tile_id - sp.tile_begin;
   const int ti = sp.tiles_j > 1 ? (int)__umulhi((unsigned)t_local, sp.tiles_j_magic) : t_local;
   const int i0 = ti * kTile;
   const int j0 = (t_local - ti * sp.tiles_j) * kTile;
@@ -552,7 +566,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_cons
     open_segment(skip * kBK);
   }
   B200_PROBE(2)
-  B200_PDL_WAIT();  // operands written by earlier kernels are read from here on
+  if (!PERSIST) B200_PDL_WAIT();  // operands written by earlier kernels are read from here on
 
   // prologue: fill kStages-1 stages
 #pragma unroll
@@ -705,21 +719,21 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_cons
   if (MODE == kFwd) {
     has0 = sp.bias != nullptr;
     has1 = act == kActTanhNoise;
-    if (live && has0) load_quad(e0, sp.bias + (long long)g * sp.bias_gs + gj0, nvalid);
-    if (live && has1) load_quad(e1, sp.aux + (long long)g * sp.aux_gs + (long long)gi * sp.aux_ld + gj0, nvalid);
+    if (live && has0) load_quad<PERSIST>(e0, sp.bias + (long long)g * sp.bias_gs + gj0, nvalid);
+    if (live && has1) load_quad<PERSIST>(e1, sp.aux + (long long)g * sp.aux_gs + (long long)gi * sp.aux_ld + gj0, nvalid);
   } else if (MODE == kDgrad) {
     has0 = sp.aux != nullptr;
     has1 = sp.accumulate != 0;
-    if (live && has0) load_quad(e0, sp.aux + (long long)g * sp.aux_gs + (long long)gi * sp.aux_ld + gj0, nvalid);
-    if (live && has1) load_quad(e1, sp.C + (long long)g * sp.c_gs + (long long)gi * sp.c_ld + gj0, nvalid);
+    if (live && has0) load_quad<PERSIST>(e0, sp.aux + (long long)g * sp.aux_gs + (long long)gi * sp.aux_ld + gj0, nvalid);
+    if (live && has1) load_quad<PERSIST>(e1, sp.C + (long long)g * sp.c_gs + (long long)gi * sp.c_ld + gj0, nvalid);
   } else {
     has0 = sp.P != nullptr;
     if (live && has0) {
       const long long off = (long long)g * sp.p_gs + (long long)gi * sp.p_ld + gj0;
-      load_quad(e0, sp.P + off, nvalid);
-      load_quad(e1, sp.M + off, nvalid);
-      load_quad(e2, sp.V + off, nvalid);
-      adam_s = *sp.adam;
+      load_quad<PERSIST>(e0, sp.P + off, nvalid);
+      load_quad<PERSIST>(e1, sp.M + off, nvalid);
+      load_quad<PERSIST>(e2, sp.V + off, nvalid);
+      adam_s = load_adam<PERSIST>(sp.adam);
     }
   }
 
@@ -836,6 +850,29 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_cons
   B200_PROBE(7)
   store_quad(sp.C + (long long)g * sp.c_gs + (long long)gi * sp.c_ld + gj0, out, nvalid);
   B200_PROBE_END
+}
+
+template <int MODE, bool MMA>
+__global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const __grid_constant__ FfmaLaunch L) {
+  B200_PDL_TRIGGER();  // the setup below reads kernel parameters only: it may overlap the previous kernel
+  B200_TIMELINE(L.tag)
+  // 3 pipeline stages x (A tile 32x64, B tile 32x64) = 48 KB; the first 32 KB later hold the 8 partial tiles;
+  // behind them one 4 KB receive slot per non-leader CTA of the split-K cluster
+  B200_DYN_SMEM(float, smem);
+  int tile_id = (int)blockIdx.x, split = 0;
+#ifndef B200_EMU
+  const int splitk = L.splitk;
+  if (splitk > 1) {
+    cluster_arrive();  // phase 1: "my shared memory exists" (waited on just before the DSMEM pushes)
+    tile_id = (int)cluster_id_x();
+    split = (int)cluster_ctarank();
+  }
+#else
+  constexpr int splitk = 1;
+#endif
+  int pi = 0;
+  while (pi + 1 < L.nprob && tile_id >= L.p[pi + 1].tile_begin) ++pi;
+  gemm_tile<MODE, MMA, false>(L.p[pi], tile_id - L.p[pi].tile_begin, (int)blockIdx.y, split, splitk, smem);
 }
 
 // ---- bias gradients of stacked seeds --------------------------------------------------------------

@@ -398,6 +398,7 @@ inline int gemm_table_launch(const GemmTable& t, int groups, cudaStream_t stream
 
 // ----------------------------------------------------------------------------- row-op tables (AvgL1Norm)
 struct RowTable {
+  std::vector<RowOp> h_ops;  // host copy (the persistent dataflow kernel records them, mega.cuh)
   RowOp* d_ops = nullptr;
   int nops = 0;
   int total_rows = 0;
@@ -417,6 +418,7 @@ inline int row_table_upload(RowTable* t, bool bwd, std::vector<RowOp>& ops, Devi
   int rows = 0;
   for (auto& o : ops) { o.row_begin = rows; rows += o.rows; }
   t->bwd = bwd;
+  t->h_ops = ops;
   t->nops = (int)ops.size();
   t->total_rows = rows;
   B200_TRY(arena->alloc(&t->d_ops, ops.size()));

@@ -31,17 +31,25 @@ struct RowOp {
 
 constexpr float kNormEps = 1e-8f;
 
-template <bool BWD>
-__global__ void __launch_bounds__(256) avgl1norm_kernel(const RowOp* __restrict__ ops, int nops, int total_rows) {
-  B200_PDL_PROLOGUE();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row_lin = blockIdx.x * 8 + warp;
-  const int g = blockIdx.y;
-  if (row_lin >= total_rows) return;
-  int oi = 0;
-  while (oi + 1 < nops && row_lin >= ops[oi + 1].row_begin) ++oi;
-  const RowOp op = ops[oi];
-  const int row = row_lin - op.row_begin;
+// loads of data another SM may have produced inside the same (persistent) kernel go through L2
+template <bool CG>
+__device__ __forceinline__ float ldf(const float* p) {
+#ifndef B200_EMU
+  if (CG) return __ldcg(p);
+#endif
+  return *p;
+}
+template <bool CG>
+__device__ __forceinline__ float4 ldf4(const float* p) {
+#ifndef B200_EMU
+  if (CG) return __ldcg(reinterpret_cast<const float4*>(p));
+#endif
+  return *reinterpret_cast<const float4*>(p);
+}
+
+// one row of one tensor, by one warp
+template <bool BWD, bool CG>
+__device__ __forceinline__ void avgl1norm_row(const RowOp& op, int row, int g, int lane) {
   const int n = op.n;
   const float* x = op.x + (long long)g * op.x_gs + (long long)row * op.x_ld;
   float* y = op.y + (long long)g * op.y_gs + (long long)row * op.y_ld;
@@ -57,8 +65,8 @@ __global__ void __launch_bounds__(256) avgl1norm_kernel(const RowOp* __restrict_
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (k < nv) {
-        xv[k] = *reinterpret_cast<const float4*>(x + k * 128 + lane * 4);
-        if (BWD) dv[k] = *reinterpret_cast<const float4*>(dy + k * 128 + lane * 4);
+        xv[k] = ldf4<CG>(x + k * 128 + lane * 4);
+        if (BWD) dv[k] = ldf4<CG>(dy + k * 128 + lane * 4);
       }
     }
 #pragma unroll
@@ -88,25 +96,38 @@ __global__ void __launch_bounds__(256) avgl1norm_kernel(const RowOp* __restrict_
     return;
   }
   for (int j = lane; j < n; j += 32) {
-    float v = x[j];
+    float v = ldf<CG>(x + j);
     s_abs += fabsf(v);
-    if (BWD) s_dot = fmaf(dy[j], v, s_dot);
+    if (BWD) s_dot = fmaf(ldf<CG>(dy + j), v, s_dot);
   }
   s_abs = warp_sum(s_abs);
   const float mean = s_abs / (float)n;
   const float c = fmaxf(mean, kNormEps);
   if (!BWD) {
-    for (int j = lane; j < n; j += 32) y[j] = x[j] / c;
+    for (int j = lane; j < n; j += 32) y[j] = ldf<CG>(x + j) / c;
   } else {
     s_dot = warp_sum(s_dot);
     // y = x / c ; c = clamp(mean|x|, eps):  dx = dy/c + sign(x) * [mean>=eps] * (-sum(dy*x)/c^2) / n
     const float gm = (mean >= kNormEps) ? (-s_dot / (c * c)) / (float)n : 0.f;
     for (int j = lane; j < n; j += 32) {
-      float v = x[j];
+      float v = ldf<CG>(x + j);
       float sg = (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f);
-      y[j] = dy[j] / c + sg * gm;
+      y[j] = ldf<CG>(dy + j) / c + sg * gm;
     }
   }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(256) avgl1norm_kernel(const RowOp* __restrict__ ops, int nops, int total_rows) {
+  B200_PDL_PROLOGUE();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_lin = blockIdx.x * 8 + warp;
+  const int g = blockIdx.y;
+  if (row_lin >= total_rows) return;
+  int oi = 0;
+  while (oi + 1 < nops && row_lin >= ops[oi + 1].row_begin) ++oi;
+  const RowOp op = ops[oi];
+  avgl1norm_row<BWD, false>(op, row_lin - op.row_begin, g, lane);
 }
 
 // ----------------------------------------------------------------------------- per-step scalars
@@ -136,9 +157,14 @@ __device__ __forceinline__ void publish_info(const StepState* st, long long g, i
 }
 
 // one thread: advance counters and refresh the Adam scalars of the optimizers that step now
+__device__ __forceinline__ void prep_step_body(StepState* st, AdamScalars* adam, const OptimHyper* hyper, int nopt, unsigned step_mask, int ring);
 __global__ void prep_step_kernel(StepState* st, AdamScalars* adam, const OptimHyper* hyper, int nopt, unsigned step_mask, int ring) {
   B200_PDL_PROLOGUE();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  prep_step_body(st, adam, hyper, nopt, step_mask, ring);
+}
+// (one thread)
+__device__ __forceinline__ void prep_step_body(StepState* st, AdamScalars* adam, const OptimHyper* hyper, int nopt, unsigned step_mask, int ring) {
   st->n_runs += 1;
   st->info_slot = (st->n_runs - 1) % ring;
   for (int k = 0; k < nopt; ++k) {

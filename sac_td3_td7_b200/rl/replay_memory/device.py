@@ -153,6 +153,8 @@ class _DeviceRing(BaseReplayMemory):
             ns = g.standard_normal((m, S), dtype=np.float32)
             dn = (g.random((m, 1), dtype=np.float32) < 0.99).astype(np.float32)
             rows = self.pack(st, ac, rw, ns, dn)
+            if self.n_seeds > 1 and not self.share_rows:
+                rows = torch.from_numpy(rows).to(self.device)  # one H2D, then a device-to-device copy into every seed's private store
             for s in range(1 if self.share_rows else self.n_seeds):
                 self.append_rows(rows, s)
             if self.share_rows:

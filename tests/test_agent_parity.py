@@ -421,3 +421,16 @@ def test_step_parity_teacher_forced_on_the_tcgen05_path(dev, name, capsys):
     assert worst["grad_fro"][0] <= TC_TOL["grad_fro"][algo], worst["grad_fro"]
     assert worst["elem"][0] <= 2.002, worst["elem"]
     assert worst["step"][0] <= TC_TOL["step_rms"], worst["step"]
+
+
+@pytest.mark.parametrize("name", ["td7_halfcheetah_lap", "td7_humanoid_lap"])
+def test_step_parity_teacher_forced_through_the_dataflow_kernels(dev, name):
+    """The optional persistent dataflow engine (csrc/mega.cuh, b200rl_set_mega): same teacher-forced protocol, same 1e-5
+    bars -- its tile order is derived from memory-rectangle overlap, so any missed dependency shows up here."""
+    if dev.backend != "cuda":
+        pytest.skip("the dataflow kernels are not emulated")
+    dev.lib.b200rl_set_mega(1)
+    try:
+        test_step_parity_teacher_forced(dev, name)
+    finally:
+        dev.lib.b200rl_set_mega(-1)
