@@ -374,6 +374,26 @@ def act_append_latency(agent, buf):
     for _ in range(n):
         agent.sample(o, True)
     act_us = (time.perf_counter() - t0) / n * 1e6
+    # the same call at the C ABI (no Python argument handling), and the kernel alone (device tensors, CUDA events)
+    from sac_td3_td7_b200 import _lib
+
+    out = np.empty((G, agent._act_out_dim), np.float32)
+    po, pout, st = obs.ctypes.data, out.ctypes.data, _lib.current_stream_ptr()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        agent._lib.b200rl_agent_act_host(agent._h, po, pout, st)
+    act_c_us = (time.perf_counter() - t0) / n * 1e6
+    d_obs, d_out = torch.as_tensor(obs).cuda(), torch.empty((G, agent._act_out_dim), device="cuda")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(10):
+        agent.policy_out_device(d_obs, d_out)
+    torch.cuda.synchronize()
+    e0.record(torch.cuda.current_stream())
+    for _ in range(n):
+        agent._lib.b200rl_agent_act(agent._h, d_obs.data_ptr(), d_out.data_ptr(), st)
+    e1.record(torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    act_kernel_us = e0.elapsed_time(e1) / n * 1e3
     a = (g.random((G, A), dtype=np.float32) * 2 - 1) * np.asarray(agent.action_scale, np.float32)
     r, nd = np.zeros(G, np.float32), np.ones(G, np.float32)
     ap = (lambda: buf.append([obs[0], a[0], 0.0, obs[0], 1.0])) if G == 1 else (lambda: buf.append_population(obs, a, r, obs, nd))
@@ -386,9 +406,9 @@ def act_append_latency(agent, buf):
     host_us = (time.perf_counter() - t0) / n * 1e6
     torch.cuda.synchronize()
     total_us = (time.perf_counter() - t0) / n * 1e6
-    return {"act_us": act_us, "append_host_us": host_us, "append_us": total_us,
+    return {"act_us": act_us, "act_c_abi_us": act_c_us, "act_kernel_us": act_kernel_us, "append_host_us": host_us, "append_us": total_us,
             "note": "act_us: agent.sample(obs, deterministic) host to host (pinned observation slot -> one cluster kernel per seed -> pinned action mailbox, no stream "
-                    "sync); append_host_us: host time of replay.append per call (asynchronous); append_us: the same including the device work (synchronised at the end)"}
+                    "sync); act_c_abi_us: b200rl_agent_act_host alone; act_kernel_us: back-to-back launches of the acting kernel on device tensors; append_host_us: host time of replay.append per call (asynchronous); append_us: the same including the device work (synchronised at the end)"}
 
 
 def single_agent_record(workload: str, K: int, with_cpu: bool, lib):
@@ -398,7 +418,7 @@ def single_agent_record(workload: str, K: int, with_cpu: bool, lib):
     S, A = ENV_DIMS[env]
     agent, buf = make_agent_and_buffer(workload, 0)
     K = max(K, MIN_SINGLE_UPDATES) if seeds == 1 else max(K, 20)
-    ms, infos, _ = timed_burst(agent, buf, K, 20 if seeds == 1 else 3)
+    ms, infos, _ = timed_burst(agent, buf, K, 300 if seeds == 1 else 3)  # (single agents: long enough for the SM clock to ramp)
     value = seeds * K / (ms / 1e3)
     e2e = e2e_loop(agent, buf, min(K, 2000) if seeds == 1 else min(K, 50), 5, 1, seeds)
     lat = act_append_latency(agent, buf)

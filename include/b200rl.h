@@ -56,8 +56,9 @@ int b200rl_stream_sync(void* stream);
 
 /* =============================================================================================
  * Replay memory -- rl/replay_memory/lap.py:12-76 (LAPReplayMemory), simple.py:12-65
- * (SimpleReplayMemory).  A transition is one packed fp32 row:
- *   [ state(S) | action(A) | reward | notdone | next_state(S) | zero pad to a multiple of 4 ]
+ * (SimpleReplayMemory).  A transition is one packed fp32 row whose observation vectors start on 16-byte boundaries:
+ *   [ state(S) pad->x4 | next_state(S) pad->x4 | action(A) | reward | notdone | zero pad to a multiple of 4 ]
+ * (b200rl_replay_row_stride / b200rl_replay_row_layout give the stride and the field offsets).
  * `groups` > 1 stacks independent seeds; with share_rows the transitions are stored once and
  * only the priority arrays are per seed.
  * ============================================================================================= */
@@ -68,6 +69,8 @@ int b200rl_replay_create(int64_t capacity, int state_dim, int action_dim, int gr
                          b200rl_replay** out);
 int b200rl_replay_destroy(b200rl_replay* h);
 int b200rl_replay_row_stride(const b200rl_replay* h);
+/* float offsets of {state, action, reward, notdone, next_state} inside a packed row */
+int b200rl_replay_row_layout(const b200rl_replay* h, int* offsets5);
 /* lap.py:31-43 (append): `count` packed rows (action already a/scale-bias); new rows take
  * priority = running max.  rows_host is host memory; *_device takes a device pointer. */
 int b200rl_replay_append(b200rl_replay* h, int group, const float* rows_host, int64_t count, void* stream);

@@ -79,6 +79,7 @@ SIGNATURES = {
     "b200rl_replay_create": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(c_vp)]),
     "b200rl_replay_destroy": (C.c_int, [c_vp]),
     "b200rl_replay_row_stride": (C.c_int, [c_vp]),
+    "b200rl_replay_row_layout": (C.c_int, [c_vp, C.POINTER(C.c_int)]),
     "b200rl_replay_append": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int64, c_vp]),
     "b200rl_replay_append_device": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int64, c_vp]),
     "b200rl_replay_set_action_norm": (C.c_int, [c_vp, c_vp, c_vp]),

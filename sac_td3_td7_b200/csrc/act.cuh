@@ -48,19 +48,32 @@ __device__ __forceinline__ void st_cluster_f32(float* local, unsigned rank, floa
 }
 
 // y[j] = act(b[j] + W[j][0:na] . xa + W[j][na:na+nb] . xb) for this CTA's share of the outputs.  dst != null: the
-// result goes into dst[j] of EVERY CTA of the cluster; gout != null: straight to global memory.
-__device__ __forceinline__ void act_matvec(const ActLayer& Lr, int g, const float* xa, int na, const float* xb, int nb, int act, float* dst, float* gout, unsigned rank) {
+// result goes into dst[j] of EVERY CTA of the cluster; gout != null: straight to global memory.  A second layer L2r
+// (same input, same output count: zs1 and l0 both read the observation) rides along so that all weight loads of the
+// phase are in flight together.
+__device__ __forceinline__ void act_matvec(const ActLayer& Lr, int g, const float* xa, int na, const float* xb, int nb, int act, float* dst, float* gout, unsigned rank,
+                                           const ActLayer* L2r = nullptr, int act2 = 0, float* dst2 = nullptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per = (Lr.out + kActCluster - 1) / kActCluster;
   const int j_lo = (int)rank * per, j_hi = min(Lr.out, j_lo + per);
   const float* W = Lr.W + (long long)g * Lr.gs;
   const float* bias = Lr.b + (long long)g * Lr.gs;
+  const float* W2 = L2r ? L2r->W + (long long)g * L2r->gs : nullptr;
+  const float* bias2 = L2r ? L2r->b + (long long)g * L2r->gs : nullptr;
   const bool vec = ((na | nb) & 3) == 0;  // both segments start 16-byte aligned in the weight row
+  const int o_fin = lane >> 3, r_fin = lane & 7;  // lane (o, r) finishes output j0 + o and delivers it to CTA r
   for (int j0 = j_lo + warp * 4; j0 < j_hi; j0 += 8 * 4) {  // four output rows per warp and round
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
     const float* wr[4];
+    const float* wr2[4];
 #pragma unroll
-    for (int o = 0; o < 4; ++o) wr[o] = W + (long long)min(j0 + o, Lr.out - 1) * Lr.ld;
+    for (int o = 0; o < 4; ++o) {
+      wr[o] = W + (long long)min(j0 + o, Lr.out - 1) * Lr.ld;
+      wr2[o] = W2 ? W2 + (long long)min(j0 + o, Lr.out - 1) * L2r->ld : nullptr;
+    }
+    const int jf = min(j0 + o_fin, Lr.out - 1);
+    const float bv = __ldg(bias + jf);  // requested before the reduction, consumed after it
+    const float bv2 = bias2 ? __ldg(bias2 + jf) : 0.f;
 #pragma unroll
     for (int sgm = 0; sgm < 2; ++sgm) {
       const float* x = sgm ? xb : xa;
@@ -70,30 +83,47 @@ __device__ __forceinline__ void act_matvec(const ActLayer& Lr, int g, const floa
 #pragma unroll 2
         for (int k = lane * 4; k < n; k += 128) {
           const float4 xv = *reinterpret_cast<const float4*>(x + k);
-          float4 wv[4];
+          float4 wv[4], wv2[4];
 #pragma unroll
           for (int o = 0; o < 4; ++o) wv[o] = __ldg(reinterpret_cast<const float4*>(wr[o] + koff + k));
+          if (W2) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) wv2[o] = __ldg(reinterpret_cast<const float4*>(wr2[o] + koff + k));
+          }
 #pragma unroll
           for (int o = 0; o < 4; ++o) acc[o] = fmaf(wv[o].x, xv.x, fmaf(wv[o].y, xv.y, fmaf(wv[o].z, xv.z, fmaf(wv[o].w, xv.w, acc[o]))));
+          if (W2) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) acc2[o] = fmaf(wv2[o].x, xv.x, fmaf(wv2[o].y, xv.y, fmaf(wv2[o].z, xv.z, fmaf(wv2[o].w, xv.w, acc2[o]))));
+          }
         }
       } else {
         for (int k = lane; k < n; k += 32) {
           const float xv = x[k];
 #pragma unroll
           for (int o = 0; o < 4; ++o) acc[o] = fmaf(__ldg(wr[o] + koff + k), xv, acc[o]);
+          if (W2) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) acc2[o] = fmaf(__ldg(wr2[o] + koff + k), xv, acc2[o]);
+          }
         }
       }
     }
 #pragma unroll
     for (int o = 0; o < 4; ++o) acc[o] = warp_sum(acc[o]);
-    // lane (o, r) = (lane >> 3, lane & 7) finishes output j0 + o and delivers it to CTA r
-    const int o = lane >> 3, r = lane & 7;
-    const int j = j0 + o;
+    if (W2) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) acc2[o] = warp_sum(acc2[o]);
+    }
+    const int j = j0 + o_fin;
     if (j < j_hi) {
-      const float s = (o == 0 ? acc[0] : o == 1 ? acc[1] : o == 2 ? acc[2] : acc[3]) + __ldg(bias + j);
-      const float y = act_forward(s, act);
-      if (dst) st_cluster_f32(dst + j, (unsigned)r, y);
-      if (gout && r == 0) gout[j] = y;
+      const float y = act_forward((o_fin == 0 ? acc[0] : o_fin == 1 ? acc[1] : o_fin == 2 ? acc[2] : acc[3]) + bv, act);
+      if (dst) st_cluster_f32(dst + j, (unsigned)r_fin, y);
+      if (gout && r_fin == 0) gout[j] = y;
+      if (W2) {
+        const float y2 = act_forward((o_fin == 0 ? acc2[0] : o_fin == 1 ? acc2[1] : o_fin == 2 ? acc2[2] : acc2[3]) + bv2, act2);
+        st_cluster_f32(dst2 + j, (unsigned)r_fin, y2);
+      }
     }
   }
 }
@@ -113,7 +143,12 @@ __device__ __forceinline__ void act_norm(float* x, int n, float* red) {
   __syncthreads();
 }
 
-__global__ void __cluster_dims__(kActCluster, 1, 1) __launch_bounds__(kActThreads) act_fused_kernel(const __grid_constant__ ActArgs a) {
+// a single agent's observation travels BY VALUE in the kernel parameters (<= 4 KB): no pinned slot, no read over the bus
+constexpr int kActInlineObs = 1024;
+struct ActObs { float v[kActInlineObs]; };
+
+template <bool INLINE_OBS>
+__global__ void __cluster_dims__(kActCluster, 1, 1) __launch_bounds__(kActThreads) act_fused_kernel(const __grid_constant__ ActArgs a, const __grid_constant__ ActObs ob) {
   B200_DYN_SMEM(float, sm);
   __shared__ float red[kActThreads / 32];
   const unsigned rank = cluster_ctarank();
@@ -123,15 +158,23 @@ __global__ void __cluster_dims__(kActCluster, 1, 1) __launch_bounds__(kActThread
   float* v1 = v0 + a.vmax;
   float* v2 = v1 + a.vmax;
   float* v3 = v2 + a.vmax;
-  const float* obs = a.obs + (long long)g * a.obs_gs;
-  for (int k = threadIdx.x; k < a.S; k += kActThreads) xo[k] = obs[k];
+  if (INLINE_OBS) {
+    for (int k = threadIdx.x; k < a.S; k += kActThreads) xo[k] = ob.v[k];
+  } else {
+    const float* obs = a.obs + (long long)g * a.obs_gs;
+    for (int k = threadIdx.x; k < a.S; k += kActThreads) xo[k] = obs[k];
+  }
   __syncthreads();
   cluster_arrive();  // every CTA of the cluster is running (its shared memory may be written) ...
   cluster_wait();
   float* out = a.out + (long long)g * a.out_gs;
   if (a.kind == 0) {
-    act_matvec(a.L[0], g, xo, a.S, nullptr, 0, kActElu, v0, nullptr, rank);   // h1 = elu(zs1 s)
-    act_matvec(a.L[3], g, xo, a.S, nullptr, 0, kActNone, v1, nullptr, rank);  // p0 = l0 s
+    if (a.L[0].out == a.L[3].out) {  // h1 = elu(zs1 s) and p0 = l0 s in one pass over the observation
+      act_matvec(a.L[0], g, xo, a.S, nullptr, 0, kActElu, v0, nullptr, rank, &a.L[3], kActNone, v1);
+    } else {
+      act_matvec(a.L[0], g, xo, a.S, nullptr, 0, kActElu, v0, nullptr, rank);
+      act_matvec(a.L[3], g, xo, a.S, nullptr, 0, kActNone, v1, nullptr, rank);
+    }
     cluster_arrive(); cluster_wait();
     act_matvec(a.L[1], g, v0, a.H, nullptr, 0, kActElu, v2, nullptr, rank);   // h2 = elu(zs2 h1)
     act_norm(v1, a.H, red);                                                   // p0n (local copy; nobody writes v1 any more)
@@ -151,7 +194,15 @@ __global__ void __cluster_dims__(kActCluster, 1, 1) __launch_bounds__(kActThread
     cluster_arrive(); cluster_wait();
     act_matvec(a.L[2], g, v1, a.H, nullptr, 0, a.kind == 1 ? kActTanh : kActNone, nullptr, out, rank);
   }
-  if (a.tag) {  // last CTA of the launch posts the sequence tag behind every seed's action
+  if (a.tag && a.total_ctas == (unsigned)kActCluster) {  // one seed: the cluster barrier orders the eight CTAs' stores, CTA 0 posts the tag
+    __syncthreads();
+    __threadfence_system();
+    cluster_arrive(); cluster_wait();
+    if (rank == 0 && threadIdx.x == 0) {
+      __threadfence_system();
+      *a.tag = a.tag_value;
+    }
+  } else if (a.tag) {  // last CTA of the launch posts the sequence tag behind every seed's action
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence_system();

@@ -132,6 +132,12 @@ int b200rl_replay_destroy(b200rl_replay* h) {
   return kOk;
 }
 int b200rl_replay_row_stride(const b200rl_replay* h) { return h ? h->r.row_stride : kErrInvalidArg; }
+int b200rl_replay_row_layout(const b200rl_replay* h, int* offsets5) {
+  B200_REQUIRE(h && offsets5, "null argument");
+  const RowLayout& L = h->r.lay;
+  offsets5[0] = L.state; offsets5[1] = L.action; offsets5[2] = L.reward; offsets5[3] = L.notdone; offsets5[4] = L.next_state;
+  return kOk;
+}
 int b200rl_replay_append(b200rl_replay* h, int group, const float* rows_host, int64_t count, void* stream) {
   B200_REQUIRE(h && rows_host, "null argument");
   return h->r.append(group, rows_host, count, cudaMemcpyHostToDevice, as_stream(stream));
@@ -319,7 +325,10 @@ static int build_act_path(b200rl_agent* h) {
   B200_CHECK_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->d_act_map), h->h_act, 0));
   B200_CHECK_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->d_tag_map), h->h_tag, 0));
   *h->h_tag = 0ull;
-  if (h->act_smem > 48 * 1024) B200_CHECK_CUDA(cudaFuncSetAttribute(act_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->act_smem));
+  if (h->act_smem > 48 * 1024) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(act_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->act_smem));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(act_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->act_smem));
+  }
 #endif
   return kOk;
 }
@@ -329,13 +338,20 @@ static inline bool use_fused_act() {
   static const bool on = [] { const char* e = getenv("B200RL_ACT_FUSED"); return e ? atoi(e) != 0 : true; }();  // 0: the launch-table path
   return on;
 }
-static int launch_act_fused(b200rl_agent* h, const float* obs, long long obs_gs, float* out, long long out_gs, bool tag, cudaStream_t s) {
+// inline_obs != null: one agent's observation by value in the kernel parameters
+static int launch_act_fused(b200rl_agent* h, const float* obs, long long obs_gs, float* out, long long out_gs, bool tag, cudaStream_t s, const float* inline_obs = nullptr) {
   ActArgs aa = h->act_args;
   aa.obs = obs; aa.obs_gs = obs_gs; aa.out = out; aa.out_gs = out_gs;
   aa.done = h->d_done;
   aa.tag = tag ? h->d_tag_map : nullptr;
   aa.tag_value = tag ? ++h->act_seq : 0ull;
-  B200_LAUNCH(act_fused_kernel, dim3((unsigned)(h->base->G * kActCluster)), dim3(kActThreads), (size_t)h->act_smem, s, aa);
+  static ActObs ob;  // (parameter block; only the first S floats are read)
+  if (inline_obs) {
+    memcpy(ob.v, inline_obs, (size_t)h->base->S * sizeof(float));
+    B200_LAUNCH(act_fused_kernel<true>, dim3((unsigned)(h->base->G * kActCluster)), dim3(kActThreads), (size_t)h->act_smem, s, aa, ob);
+  } else {
+    B200_LAUNCH(act_fused_kernel<false>, dim3((unsigned)(h->base->G * kActCluster)), dim3(kActThreads), (size_t)h->act_smem, s, aa, ob);
+  }
   B200_CHECK_LAUNCH();
   return kOk;
 }
@@ -662,8 +678,12 @@ int b200rl_agent_act_host(b200rl_agent* h, const float* obs_host, float* out_hos
   const int G = a.G, Aout = h->aout.cols;
 #ifndef B200_EMU
   if (use_fused_act()) {
-    memcpy(h->h_obs, obs_host, (size_t)G * a.S * sizeof(float));
-    B200_TRY(launch_act_fused(h, h->d_obs_map, a.S, h->d_act_map, Aout, true, s));
+    if (G == 1 && a.S <= kActInlineObs) {
+      B200_TRY(launch_act_fused(h, nullptr, 0, h->d_act_map, Aout, true, s, obs_host));
+    } else {
+      memcpy(h->h_obs, obs_host, (size_t)G * a.S * sizeof(float));
+      B200_TRY(launch_act_fused(h, h->d_obs_map, a.S, h->d_act_map, Aout, true, s));
+    }
     const volatile unsigned long long* tag = h->h_tag;
     const unsigned long long want = h->act_seq;
     const auto t0 = std::chrono::steady_clock::now();

@@ -5,9 +5,9 @@
 //           float32; v = u * P[-1] (float32); ind = first i with P[i] >= v; gather 5 arrays.
 //   update_priority (lap.py:66-69), reset_max_priority (lap.py:71-73), append (lap.py:31-43).
 //
-// HBM layout: one packed fp32 row per transition, padded to a multiple of 4 floats so a
-// warp reads it with coalesced 128-bit loads:
-//     [ state(S) | action(A) | reward | notdone | next_state(S) | pad ]
+// HBM layout: one packed fp32 row per transition; both observation vectors start on a 16-byte boundary and the row is
+// a multiple of 4 floats, so a warp reads them with coalesced 128-bit loads:
+//     [ state(S) pad4 | next_state(S) pad4 | action(A) | reward | notdone | pad4 ]      (RowLayout below)
 // (fp32 storage is value-identical to the reference's fp64-store + fp32-cast).
 // priority: fp32[capacity] (+pad) per stacked seed; max_priority: one fp32 per seed, on device.
 //
@@ -35,6 +35,7 @@ namespace b200rl {
 constexpr int kPrioTile = 256;       // priorities per tile (one warp: 32 lanes x 8)
 constexpr int kPrioTilesPerCta = 8;  // 2048 priorities per CTA in the rebuild kernel
 constexpr int kSuperTiles = 64;      // tiles per super-tile (one warp: 32 lanes x 2)
+constexpr int kSmallRowFloats = 128; // packed rows up to this many floats are gathered through one 128-bit load per lane
 
 __device__ __forceinline__ float4 ld_cg4(const float* p) {
 #ifdef B200_EMU
@@ -157,6 +158,21 @@ __global__ void __launch_bounds__(1024) lap_fix_sums_kernel(FixArgs a) {
   lap_fix_block(a, blockIdx.x);
 }
 
+// offsets (floats) of the five fields inside a packed row
+struct RowLayout {
+  int state, next_state, action, reward, notdone, stride;
+  static RowLayout make(int S, int A) {
+    RowLayout L;
+    L.state = 0;
+    L.next_state = (int)((S + 3) / 4 * 4);
+    L.action = 2 * L.next_state;
+    L.reward = L.action + A;
+    L.notdone = L.reward + 1;
+    L.stride = (L.notdone + 1 + 3) / 4 * 4;
+    return L;
+  }
+};
+
 struct SampleArgs {
   const float* priority; long long prio_gs;
   const double* tile_sums; long long ts_gs; int ntiles;
@@ -166,6 +182,7 @@ struct SampleArgs {
   unsigned long long seed, counter;        // Philox stream when u == null
   const int* counter_ptr;                  // optional device-side counter added to `counter` (graph replays)
   const float* rows; long long rows_gs; int row_stride; int S, A;
+  RowLayout lay;
   long long* idx_out; long long idx_gs;
   float* state; int ld_state; long long state_gs;
   float* action; int ld_action; long long action_gs;
@@ -265,18 +282,27 @@ __global__ void __launch_bounds__(256, kMinCtas) lap_sample_kernel(SampleArgs a)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int size = a.size;
   const int b = blockIdx.x * 8 + warp;
-  if (b >= a.B) return;
 
+  // one Philox block yields four uniforms: the CTA's eight draws need two blocks, computed by two lanes and shared (every
+  // warp recomputing its own block was ~10 % of the instructions of a draw on narrow rows)
+  __shared__ float u_sh[8];
+  __shared__ __align__(16) float row_sh[8][kSmallRowFloats];
   float u;
   if (a.u) {
-    u = a.u[(long long)g * a.u_gs + b];
+    u = b < a.B ? a.u[(long long)g * a.u_gs + b] : 0.f;
   } else {
-    Philox ph(a.seed);
-    uint32_t r[4];
-    const unsigned long long ctr = a.counter + (a.counter_ptr ? (unsigned long long)(unsigned)(*a.counter_ptr) : 0ULL);
-    ph(ctr, ((unsigned long long)g << 32) | (unsigned)(b >> 2), r);
-    u = u01_from_bits(r[b & 3]);
+    if (tid < 2) {
+      Philox ph(a.seed);
+      uint32_t r[4];
+      const unsigned long long ctr = a.counter + (a.counter_ptr ? (unsigned long long)(unsigned)(*a.counter_ptr) : 0ULL);
+      ph(ctr, ((unsigned long long)g << 32) | (unsigned)(blockIdx.x * 2 + tid), r);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u_sh[tid * 4 + k] = u01_from_bits(r[k]);
+    }
+    __syncthreads();
+    u = u_sh[warp];
   }
+  if (b >= a.B) return;
 
   long long idx;
   if (a.prioritized) {
@@ -356,14 +382,40 @@ __global__ void __launch_bounds__(256, kMinCtas) lap_sample_kernel(SampleArgs a)
   // ---- gather the packed row into the five batch tensors ----
   const float* row = a.rows + (long long)g * a.rows_gs + idx * (long long)a.row_stride;
   const int S = a.S, A = a.A;
-  if (lane == 0) {
-    a.reward[(long long)g * a.reward_gs + b] = __ldg(row + S + A);
-    a.done[(long long)g * a.done_gs + b] = __ldg(row + S + A + 1);
+  if (a.row_stride <= kSmallRowFloats) {
+    // narrow rows (<= 512 B: every MuJoCo task but Humanoid): ONE 128-bit load per lane brings the whole packed row into
+    // the warp's shared-memory slot, then each batch tensor row is written lane-per-float, coalesced
+    float* rs = row_sh[warp];
+    if (lane * 4 < a.row_stride) *reinterpret_cast<float4*>(rs + lane * 4) = __ldg(reinterpret_cast<const float4*>(row) + lane);
+    __syncwarp();
+    float* ds = a.state + (long long)g * a.state_gs + (long long)b * a.ld_state;
+    float* dn = a.next_state + (long long)g * a.next_gs + (long long)b * a.ld_next;
+    float* da = a.action + (long long)g * a.action_gs + (long long)b * a.ld_action;
+    for (int i = lane; i < S; i += 32) {
+      ds[i] = rs[a.lay.state + i];
+      dn[i] = rs[a.lay.next_state + i];
+    }
+    if (lane < A) da[lane] = rs[a.lay.action + lane];
+    for (int i = 32 + lane; i < A; i += 32) da[i] = rs[a.lay.action + i];
+    if (lane == 0) {
+      a.reward[(long long)g * a.reward_gs + b] = rs[a.lay.reward];
+      a.done[(long long)g * a.done_gs + b] = rs[a.lay.notdone];
+    }
+    return;
   }
-  warp_copy_row_segment(a.state + (long long)g * a.state_gs + (long long)b * a.ld_state, row, S, lane);
-  warp_copy_row_segment(a.next_state + (long long)g * a.next_gs + (long long)b * a.ld_next, row + S + A + 2, S, lane);
-  warp_copy_row_segment(a.action + (long long)g * a.action_gs + (long long)b * a.ld_action, row + S, A, lane);
+  if (lane == 0) {
+    a.reward[(long long)g * a.reward_gs + b] = __ldg(row + a.lay.reward);
+    a.done[(long long)g * a.done_gs + b] = __ldg(row + a.lay.notdone);
+  }
+  warp_copy_row_segment(a.state + (long long)g * a.state_gs + (long long)b * a.ld_state, row + a.lay.state, S, lane);
+  warp_copy_row_segment(a.next_state + (long long)g * a.next_gs + (long long)b * a.ld_next, row + a.lay.next_state, S, lane);
+  warp_copy_row_segment(a.action + (long long)g * a.action_gs + (long long)b * a.ld_action, row + a.lay.action, A, lane);
 }
+
+// (An eight-lanes-per-draw variant of the walk -- every lane summing a contiguous eighth of a node, 3-step scans, four
+// draws per warp instruction -- was built for the narrow rows, where this kernel is bound by instruction issue, and
+// measured on 256 stacked Ant seeds: 80.9 us against 45.3 us.  The per-element fp64 work is the same per draw either
+// way, only the scans shrink, and the serial per-lane chains halve the occupancy: dropped.  profiles/README.md.)
 
 __global__ void __launch_bounds__(1024) lap_update_priority_kernel(float* __restrict__ priority, long long prio_gs, float* __restrict__ max_priority,
                                                                    const long long* __restrict__ idx, long long idx_gs, const float* __restrict__ prio,
@@ -408,7 +460,7 @@ struct AppendArgs {
   float* priority; long long prio_gs;
   const float* max_priority;
   const float* act_scale; const float* act_bias;
-  int S, A;
+  int act_off, A;  // offset of the action columns inside a row
   FixArgs fix;  // base pointers of group 0, per-group strides inside
 };
 __global__ void __launch_bounds__(1024) lap_append_fix_kernel(AppendArgs a) {
@@ -428,7 +480,7 @@ __global__ void __launch_bounds__(1024) lap_append_fix_kernel(AppendArgs a) {
       __syncthreads();  // the action columns were just written by other threads of this block
       for (int i = threadIdx.x; i < fix.n * a.A; i += blockDim.x) {
         const int r = i / a.A, j = i - r * a.A;
-        float* p = dst_base + ((fix.pos + r) % fix.cap) * a.row_stride + a.S + j;
+        float* p = dst_base + ((fix.pos + r) % fix.cap) * a.row_stride + a.act_off + j;
         *p = __fsub_rn(__fdiv_rn(*p, a.act_scale[j]), a.act_bias[j]);
       }
     }
@@ -446,6 +498,7 @@ __global__ void __launch_bounds__(1024) lap_append_fix_kernel(AppendArgs a) {
 struct Replay {
   long long capacity = 0, cap_pad = 0;
   int S = 0, A = 0, row_stride = 0;
+  RowLayout lay;
   int groups = 1;
   bool prioritized = true;
   bool share_rows = false;
@@ -523,11 +576,11 @@ struct Replay {
     const int nrows = (n == 1 || share_rows) ? 1 : groups;
     for (int r = 0; r < nrows; ++r) {
       float* row = slot + (long long)r * row_stride;
-      memcpy(row, obs + (long long)r * S, S * sizeof(float));
-      memcpy(row + S, action + (long long)r * A, A * sizeof(float));
-      row[S + A] = reward[r];
-      row[S + A + 1] = notdone[r];
-      memcpy(row + S + A + 2, next_obs + (long long)r * S, S * sizeof(float));
+      memcpy(row + lay.state, obs + (long long)r * S, S * sizeof(float));
+      memcpy(row + lay.action, action + (long long)r * A, A * sizeof(float));
+      row[lay.reward] = reward[r];
+      row[lay.notdone] = notdone[r];
+      memcpy(row + lay.next_state, next_obs + (long long)r * S, S * sizeof(float));
     }
     int st;
     if (n == 1 && groups > 1) st = append(g, slot, 1, cudaMemcpyHostToDevice, stream, raw_action);
@@ -550,7 +603,8 @@ struct Replay {
     B200_REQUIRE(cap > 0 && s > 0 && a > 0 && g > 0, "replay: capacity, dims and groups must be positive");
     B200_REQUIRE(cap < (1LL << 31) - 4096, "replay: capacity must fit in int32");
     capacity = cap; S = s; A = a; groups = g; prioritized = prio; share_rows = share;
-    row_stride = (int)round_up(2 * S + A + 2, 4);
+    lay = RowLayout::make(S, A);
+    row_stride = lay.stride;
     cap_pad = round_up(capacity, kPrioTile * kPrioTilesPerCta);
     max_tiles = (int)round_up(cap_pad / kPrioTile, kSuperTiles);
     max_supers = max_tiles / kSuperTiles;
@@ -624,7 +678,7 @@ struct Replay {
         a.priority = prioritized ? d_priority : nullptr; a.prio_gs = cap_pad;
         a.max_priority = d_max_priority;
         if (normalise) { a.act_scale = d_act_scale; a.act_bias = d_act_bias; }
-        a.S = S; a.A = A;
+        a.act_off = lay.action; a.A = A;
         if (share_rows && g > 0) a.src = nullptr;
         B200_LAUNCH(lap_append_fix_kernel, dim3(1), dim3(count <= 32 ? 64 : 1024), 0, stream, a);
       } else {
@@ -662,7 +716,7 @@ struct Replay {
     a.priority = prioritized ? d_priority : nullptr; a.prio_gs = cap_pad;
     a.max_priority = d_max_priority;
     if (normalise) { a.act_scale = d_act_scale; a.act_bias = d_act_bias; }
-    a.S = S; a.A = A;
+    a.act_off = lay.action; a.A = A;
     B200_LAUNCH(lap_append_fix_kernel, dim3((unsigned)groups), dim3(count <= 32 ? 64 : 1024), 0, stream, a);
     B200_CHECK_LAUNCH();
     for (int g = 0; g < groups; ++g) {
@@ -745,7 +799,7 @@ struct Replay {
     a.size = (int)n;
     a.u = u_dev; a.u_gs = B;
     a.seed = rng_seed; a.counter = counter_ptr ? 0ULL : rng_counter++; a.counter_ptr = counter_ptr;
-    a.rows = d_rows; a.rows_gs = rows_gs(); a.row_stride = row_stride; a.S = S; a.A = A;
+    a.rows = d_rows; a.rows_gs = rows_gs(); a.row_stride = row_stride; a.S = S; a.A = A; a.lay = lay;
     a.idx_out = d_idx; a.idx_gs = max_batch;
     a.state = o.state; a.ld_state = o.ld_state; a.state_gs = o.state_gs;
     a.action = o.action; a.ld_action = o.ld_action; a.action_gs = o.action_gs;

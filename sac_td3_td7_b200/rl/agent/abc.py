@@ -90,6 +90,7 @@ class Agent(ABC):
         self._info_cache = {}
         self._spilled = 0
         self._inbox = None
+        self._act_io = None
         self._create_engine()
         self._push()
 
@@ -323,12 +324,13 @@ class Agent(ABC):
         memo[id(self)] = new
         self._pull()
         for k, v in self.__dict__.items():
-            if k in ("_h", "_lib", "_info_cache", "_inbox"):
+            if k in ("_h", "_lib", "_info_cache", "_inbox", "_act_io"):
                 continue
             setattr(new, k, copy.deepcopy(v, memo))
         new._lib = self._lib
         new._h = None
         new._inbox = None
+        new._act_io = None
         new._info_cache = {}
         new._spilled = new._n_calls
         new._create_engine()
@@ -340,7 +342,7 @@ class Agent(ABC):
     # materialised as plain tensors
     def __getstate__(self):
         self._pull()
-        d = {k: v for k, v in self.__dict__.items() if k not in ("_h", "_lib", "_info_cache", "_inbox")}
+        d = {k: v for k, v in self.__dict__.items() if k not in ("_h", "_lib", "_info_cache", "_inbox", "_act_io")}
         extra = {}
         if self._h:
             self._flush()
@@ -359,7 +361,7 @@ class Agent(ABC):
     def __setstate__(self, d):
         extra = d.pop("_pickled_engine_state", {})
         self.__dict__.update(d)
-        self._h, self._info_cache, self._inbox = None, {}, None
+        self._h, self._info_cache, self._inbox, self._act_io = None, {}, None, None
         self._lib = _lib.lib()
         self._create_engine()
         self._push()
@@ -484,19 +486,24 @@ class Agent(ABC):
         """Raw policy output for one observation per stacked seed, host to host through ONE kernel
         (b200rl_agent_act_host).  `state`: [S] (a single agent, or the same observation for every stacked seed) or
         [n_seeds, S]; returns [A_out] for a single agent, [n_seeds, A_out] for a population."""
-        self._flush()
-        G, S = self.n_seeds, self.state_dim
+        if self._dirty_host:
+            self._flush()
         if isinstance(state, torch.Tensor):
             state = state.detach().cpu().numpy()
-        obs = np.asarray(state, np.float32)
-        if obs.size == S:
-            obs = np.broadcast_to(obs.reshape(1, S), (G, S))
-        elif obs.shape != (G, S):
-            raise ValueError(f"observation must have shape ({S},) or ({G}, {S}), got {obs.shape}")
-        obs = np.ascontiguousarray(obs)
-        out = np.empty((G, self._act_out_dim), np.float32)
-        _lib.check(self._lib.b200rl_agent_act_host(self._h, obs.ctypes.data, out.ctypes.data, _stream()))
-        return out[0] if G == 1 else out
+        io = self._act_io
+        if io is None:
+            G, S = self.n_seeds, self.state_dim
+            obs, out = np.empty((G, S), np.float32), np.empty((G, self._act_out_dim), np.float32)
+            io = self._act_io = (obs, out, obs.ctypes.data, out.ctypes.data)
+        obs, out, p_obs, p_out = io
+        if np.size(state) == obs.shape[1]:
+            obs[:] = np.reshape(state, (1, -1))  # [S], broadcast over the stacked seeds (dtype cast by the assignment)
+        elif np.shape(state) == obs.shape:
+            obs[:] = state
+        else:
+            raise ValueError(f"observation must have shape ({obs.shape[1]},) or {obs.shape}, got {np.shape(state)}")
+        _lib.check(self._lib.b200rl_agent_act_host(self._h, p_obs, p_out, _stream()))
+        return out[0].copy() if out.shape[0] == 1 else out.copy()
 
     def policy_out_device(self, obs: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """The same forward on device tensors, asynchronously on the current stream: obs [n_seeds, S] (CUDA, fp32,

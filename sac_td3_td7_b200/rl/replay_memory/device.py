@@ -42,6 +42,9 @@ class _DeviceRing(BaseReplayMemory):
                                                       int(self.prioritized), int(self.share_rows), C.byref(h)))
         self._h = h
         self.row_stride = self._lib.b200rl_replay_row_stride(self._h)
+        offs = (C.c_int * 5)()
+        _lib.check(self._lib.b200rl_replay_row_layout(self._h, offs))
+        self.row_offsets = dict(zip(("state", "action", "reward", "done", "next_state"), offs))  # float offsets inside a packed row
         self.ptr = 0
         self.size = 0
         self._last_batch = 0
@@ -71,13 +74,20 @@ class _DeviceRing(BaseReplayMemory):
         """Packed fp32 rows [n, row_stride] from already-normalised columns."""
         state = np.asarray(state, np.float32).reshape(-1, self.state_dim)
         n, S, A = state.shape[0], self.state_dim, self.action_dim
+        o = self.row_offsets
         rows = np.zeros((n, self.row_stride), np.float32)
-        rows[:, :S] = state
-        rows[:, S:S + A] = np.asarray(action, np.float32).reshape(n, A)
-        rows[:, S + A] = np.asarray(reward, np.float32).reshape(n)
-        rows[:, S + A + 1] = np.asarray(float_done, np.float32).reshape(n)
-        rows[:, S + A + 2:2 * S + A + 2] = np.asarray(next_state, np.float32).reshape(n, S)
+        rows[:, o["state"]:o["state"] + S] = state
+        rows[:, o["action"]:o["action"] + A] = np.asarray(action, np.float32).reshape(n, A)
+        rows[:, o["reward"]] = np.asarray(reward, np.float32).reshape(n)
+        rows[:, o["done"]] = np.asarray(float_done, np.float32).reshape(n)
+        rows[:, o["next_state"]:o["next_state"] + S] = np.asarray(next_state, np.float32).reshape(n, S)
         return rows
+
+    def unpack(self, rows: np.ndarray) -> dict:
+        """The five columns of packed rows [n, row_stride] (inverse of pack)."""
+        S, A, o = self.state_dim, self.action_dim, self.row_offsets
+        return dict(state=rows[:, o["state"]:o["state"] + S], action=rows[:, o["action"]:o["action"] + A], reward=rows[:, o["reward"]:o["reward"] + 1],
+                    done=rows[:, o["done"]:o["done"] + 1], next_state=rows[:, o["next_state"]:o["next_state"] + S])
 
     def append(self, transition: list[Any], seed: int = 0) -> None:
         """lap.py:31-43 -- one transition [obs, action(env units), reward, next_obs, notdone].

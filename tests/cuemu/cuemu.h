@@ -308,15 +308,19 @@ static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
-template <class T> static inline T __shfl_sync(unsigned, T v, int src, int = 32) { return cuemu::shfl_from(v, src); }
-template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m, int = 32) { return cuemu::shfl_from(v, cuemu::cur_lane() ^ m); }
-template <class T> static inline T __shfl_down_sync(unsigned, T v, unsigned d, int = 32) {
-  int l = cuemu::cur_lane();
-  return cuemu::shfl_from(v, (l + (int)d) > 31 ? l : l + (int)d);
+// (width = segment size, a power of two: lanes exchange within their own segment, like the hardware)
+template <class T> static inline T __shfl_sync(unsigned, T v, int src, int width = 32) {
+  const int l = cuemu::cur_lane(), seg = l & ~(width - 1);
+  return cuemu::shfl_from(v, seg + (src & (width - 1)));
 }
-template <class T> static inline T __shfl_up_sync(unsigned, T v, unsigned d, int = 32) {
-  int l = cuemu::cur_lane();
-  return cuemu::shfl_from(v, (l - (int)d) < 0 ? l : l - (int)d);
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m, int = 32) { return cuemu::shfl_from(v, cuemu::cur_lane() ^ m); }
+template <class T> static inline T __shfl_down_sync(unsigned, T v, unsigned d, int width = 32) {
+  const int l = cuemu::cur_lane(), seg = l & ~(width - 1);
+  return cuemu::shfl_from(v, (l + (int)d) > seg + width - 1 ? l : l + (int)d);
+}
+template <class T> static inline T __shfl_up_sync(unsigned, T v, unsigned d, int width = 32) {
+  const int l = cuemu::cur_lane(), seg = l & ~(width - 1);
+  return cuemu::shfl_from(v, (l - (int)d) < seg ? l : l - (int)d);
 }
 static inline unsigned __ballot_sync(unsigned, int pred) {
   cuemu::Warp& w = cuemu::cur_warp();

@@ -80,13 +80,19 @@ class Dev:
         n, S = state.shape
         A = action.shape[1]
         stride = self.lib.b200rl_replay_row_stride(h)
+        o = self.row_offsets(h)
         rows = np.zeros((n, stride), np.float32)
-        rows[:, :S] = state
-        rows[:, S:S + A] = action
-        rows[:, S + A] = np.asarray(reward).reshape(n)
-        rows[:, S + A + 1] = np.asarray(notdone).reshape(n)
-        rows[:, S + A + 2:2 * S + A + 2] = next_state
+        rows[:, o["state"]:o["state"] + S] = state
+        rows[:, o["action"]:o["action"] + A] = action
+        rows[:, o["reward"]] = np.asarray(reward).reshape(n)
+        rows[:, o["done"]] = np.asarray(notdone).reshape(n)
+        rows[:, o["next_state"]:o["next_state"] + S] = next_state
         return rows
+
+    def row_offsets(self, h) -> dict:
+        offs = (C.c_int * 5)()
+        self.check(self.lib.b200rl_replay_row_layout(h, offs))
+        return dict(zip(("state", "action", "reward", "done", "next_state"), offs))
 
     def replay_append(self, h, rows: np.ndarray, group=0):
         rows = np.ascontiguousarray(rows, np.float32)

@@ -230,7 +230,8 @@ def test_population_per_step_training_through_the_python_api():
     rows = np.empty((1, b1.row_stride), np.float32)
     for g in range(G):
         b1._lib.b200rl_replay_read_rows(b1._h, g, 1504, 1, rows.ctypes.data, None)
-        assert np.array_equal(rows[0, :S], tr[0][g]) and np.array_equal(rows[0, S:S + A], tr[1][g])
+        u = b1.unpack(rows)
+        assert np.array_equal(u["state"][0], tr[0][g]) and np.array_equal(u["action"][0], tr[1][g]) and np.array_equal(u["next_state"][0], tr[3][g])
 
 
 def test_append_normalises_actions_on_the_device_bit_exactly():
@@ -254,7 +255,9 @@ def test_append_normalises_actions_on_the_device_bit_exactly():
         want.append(np.concatenate([obs.astype(np.float32), np.asarray(ref_a, np.float32), [np.float32(r), np.float32(nd)], nxt.astype(np.float32)]))
     rows = np.empty((40, buf.row_stride), np.float32)
     buf._lib.b200rl_replay_read_rows(buf._h, 0, 0, 40, rows.ctypes.data, None)
-    assert np.array_equal(rows[:, :2 * S + A + 2], np.stack(want))
+    u = buf.unpack(rows)
+    got = np.concatenate([u["state"], u["action"], u["reward"], u["done"], u["next_state"]], 1)
+    assert np.array_equal(got, np.stack(want))
     assert buf.size == 40 and len(buf) == 40
     assert torch.equal(buf.priority[:40], torch.ones(40))
 

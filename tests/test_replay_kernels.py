@@ -92,9 +92,11 @@ def test_append_ring_wrap_scatter_and_running_max(dev):
     stride = dev.lib.b200rl_replay_row_stride(h)
     rows = np.empty((cap, stride), np.float32)
     dev.check(dev.lib.b200rl_replay_read_rows(h, 0, 0, cap, rows.ctypes.data, None))
-    assert np.array_equal(rows[:, :S], ref.state.astype(np.float32))
-    assert np.array_equal(rows[:, S:S + A], ref.action.astype(np.float32))
-    assert np.array_equal(rows[:, S + A + 2:2 * S + A + 2], ref.next_state.astype(np.float32))
+    o = dev.row_offsets(h)
+    assert np.array_equal(rows[:, o["state"]:o["state"] + S], ref.state.astype(np.float32))
+    assert np.array_equal(rows[:, o["action"]:o["action"] + A], ref.action.astype(np.float32))
+    assert np.array_equal(rows[:, o["next_state"]:o["next_state"] + S], ref.next_state.astype(np.float32))
+    assert o["next_state"] % 4 == 0 and o["state"] == 0  # both observation vectors on 16-byte boundaries
     dev.check(dev.lib.b200rl_replay_destroy(h))
 
 
