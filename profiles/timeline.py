@@ -20,7 +20,7 @@ from sac_td3_td7_b200.rl.replay_memory import LAPReplayMemory  # noqa: E402
 lib = _lib.lib()
 algo = sys.argv[1] if len(sys.argv) > 1 else "TD7"
 if algo == "TD7":
-    env = "HalfCheetah-v4"
+    env = os.environ.get("TIMELINE_ENV", "HalfCheetah-v4")
     agent = TD7(env, use_lap=True)
     buf = LAPReplayMemory(1_000_000, env)
 elif algo == "TD3":

@@ -153,7 +153,7 @@ struct AgentBase {
 #ifndef B200_EMU
   // the persistent dataflow path (mega.cuh): an option (B200RL_MEGA=1 / b200rl_set_mega), single agents only (stacked
   // seeds share the step counters, which the per-seed counters of the dataflow kernel do not order).  It is parity-green
-  // but NOT the default: measured on B200 a TD7 update takes 382 us through it against 205 us through the
+  // but NOT the default: measured on B200 a TD7 update takes 345 us through it (382 us before the descriptor table moved to kernel parameters) against 203 us through the
   // launch-per-layer graphs -- the 32 x 32 FFMA tile sustains ~28 tiles/us machine-wide either way (20 % of the fp32
   // peak, shared-memory fragment traffic), the classic graphs already keep the machine that busy with 2.4 launches in
   // flight, and the dataflow kernel adds ~3 us of ticket / descriptor / counter traffic per tile (profiles/README.md).

@@ -28,6 +28,7 @@
 #pragma once
 #ifndef B200_EMU
 #include <map>
+#include <memory>
 #include <set>
 
 #include "gemm.cuh"
@@ -54,17 +55,28 @@ union MegaDesc {
   GaussArgs gauss;
   int words[(sizeof(FfmaProblem) + 3) / 4];
 };
-struct MegaTile {
+struct MegaWait { int flag; unsigned need; };
+constexpr int kMegaInlineWaits = 4;
+struct MegaTile {  // 64 bytes
   int kind, desc, t_local;
   int signal, signal2;  // counters bumped when the tile is done: its row-block group and its whole node (-1: none)
-  int nwait, wait_first;
+  int nwait, wait_first;  // waits beyond the inline ones live in MegaArgs::waits[wait_first + (i - kMegaInlineWaits)]
   int pad;
+  MegaWait w[kMegaInlineWaits];  // the first waits travel with the tile record: no dependent load before polling
 };
-struct MegaWait { int flag; unsigned need; };
+// every node's descriptor travels in kernel-parameter (constant) memory: the tile bodies address their problem through
+// the constant bank like the classic kernels do, instead of spending registers on a shared-memory copy
+constexpr int kMegaMaxGemm = 88, kMegaMaxRows = 36;
+struct MegaDescTable {  // < 32 KB of kernel parameters; a tile's `desc` indexes the array of its kind
+  FfmaProblem gemm[kMegaMaxGemm];
+  RowOp rows[kMegaMaxRows];
+  PrepArgs prep;
+  GaussArgs gauss[2];
+};
+static_assert(sizeof(MegaDescTable) + 64 <= 32000, "descriptor table must fit the kernel-parameter space");
 struct MegaArgs {
   const MegaTile* tiles;
   const MegaWait* waits;
-  const MegaDesc* descs;
   unsigned* flags;  // [groups][nflags]
   unsigned* ctrl;   // [0] next tile, [1] CTAs that have left, [2] launches completed, [3] error word
   int ntiles, nflags, groups, pad;
@@ -113,33 +125,42 @@ __device__ __forceinline__ unsigned mega_smid() {
 
 // (each mode gets its own register allocation: inlined into one body the three tile bodies spill)
 template <int MODE, bool MMA>
-__device__ __noinline__ void mega_gemm_tile(const FfmaProblem& sp, int t_local, int g, float* smem) {
+__device__ __forceinline__ void mega_gemm_tile(const FfmaProblem& sp, int t_local, int g, float* smem) {
   gemm_tile<MODE, MMA, true>(sp, t_local, g, 0, 1, smem);
 }
 
 template <bool MMA>
-__global__ void __launch_bounds__(kGemmThreads, 2) mega_kernel(const MegaArgs a) {
+__global__ void __launch_bounds__(kGemmThreads, 2) mega_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ MegaDescTable D) {
   B200_DYN_SMEM(float, smem);
-  __shared__ MegaDesc desc;
-  __shared__ MegaTile cur;
+  __shared__ MegaTile cur[2];  // double-buffered: the record of the NEXT tile is fetched while the current one computes
   __shared__ int next_v;
   const int tid = threadIdx.x;
   const int total = a.ntiles * a.groups;
   const unsigned epoch1 = __ldcg(a.ctrl + 2) + 1u;  // stable during the launch: only the last CTA to leave bumps it
-  if (tid == 0) next_v = (int)atomicAdd(a.ctrl, 1u);
+  if (tid < 16) {
+    int v0 = 0;
+    if (tid == 0) v0 = (int)atomicAdd(a.ctrl, 1u);
+    v0 = __shfl_sync(0xffffu, v0, 0);
+    if (tid == 0) next_v = v0;
+    if (v0 < total) reinterpret_cast<int*>(&cur[0])[tid] = __ldg(reinterpret_cast<const int*>(a.tiles + v0 / a.groups) + tid);
+  }
   __syncthreads();
-  int v = next_v;
+  int v = next_v, buf = 0;
   while (v < total) {
     const int t = v / a.groups, g = v - t * a.groups;
-    __syncthreads();  // everybody has read next_v / finished the previous tile's shared memory
+    (void)t;
     MEGA_TRACE(0)
-    if (tid < 8) reinterpret_cast<int*>(&cur)[tid] = __ldg(reinterpret_cast<const int*>(a.tiles + t) + tid);
-    if (tid == 32) next_v = (int)atomicAdd(a.ctrl, 1u);  // the next tile's ticket, off the critical path
-    __syncthreads();
-    const MegaTile tl = cur;
-    for (int i = tid; i < (int)(sizeof(MegaDesc) / 4); i += kGemmThreads) desc.words[i] = __ldg(reinterpret_cast<const int*>(a.descs + tl.desc) + i);
+    const MegaTile& tl = cur[buf];
+    if (tid >= 32 && tid < 48) {  // the next ticket and its tile record, off the critical path (warp 1)
+      const int l = tid - 32;
+      int nv = 0;
+      if (l == 0) nv = (int)atomicAdd(a.ctrl, 1u);
+      nv = __shfl_sync(0xffffu, nv, 0);
+      if (l == 0) next_v = nv;
+      if (nv < total) reinterpret_cast<int*>(&cur[buf ^ 1])[l] = __ldg(reinterpret_cast<const int*>(a.tiles + nv / a.groups) + l);
+    }
     if (tid < tl.nwait) {
-      const MegaWait w = a.waits[tl.wait_first + tid];
+      const MegaWait w = tid < kMegaInlineWaits ? tl.w[tid] : a.waits[tl.wait_first + tid - kMegaInlineWaits];
       const unsigned* f = a.flags + (size_t)g * a.nflags + w.flag;
       const unsigned target = epoch1 * w.need;
       long long spins = 0;
@@ -155,31 +176,35 @@ __global__ void __launch_bounds__(kGemmThreads, 2) mega_kernel(const MegaArgs a)
     }
     __syncthreads();
     MEGA_TRACE(1)
-    switch (tl.kind) {
-      case kMegaFwd: mega_gemm_tile<kFwd, MMA>(desc.gemm, tl.t_local, g, smem); break;
-      case kMegaDgrad: mega_gemm_tile<kDgrad, MMA>(desc.gemm, tl.t_local, g, smem); break;
-      case kMegaWgrad: mega_gemm_tile<kWgrad, MMA>(desc.gemm, tl.t_local, g, smem); break;
+    const int kind = tl.kind, t_local = tl.t_local, di = tl.desc;
+    switch (kind) {
+      case kMegaFwd: mega_gemm_tile<kFwd, MMA>(D.gemm[di], t_local, g, smem); break;
+#ifndef MEGA_ONLY_FWD
+      case kMegaDgrad: mega_gemm_tile<kDgrad, MMA>(D.gemm[di], t_local, g, smem); break;
+      case kMegaWgrad: mega_gemm_tile<kWgrad, MMA>(D.gemm[di], t_local, g, smem); break;
+#endif
       case kMegaNormFwd:
       case kMegaNormBwd: {
         const int warp = tid >> 5, lane = tid & 31;
+        const RowOp& op = D.rows[di];
 #pragma unroll 1
         for (int k = 0; k < kMegaRowsPerTile / 8; ++k) {
-          const int row = tl.t_local * kMegaRowsPerTile + k * 8 + warp;
-          if (row < desc.rows.rows) {
-            if (tl.kind == kMegaNormFwd) avgl1norm_row<false, true>(desc.rows, row, g, lane);
-            else avgl1norm_row<true, true>(desc.rows, row, g, lane);
+          const int row = t_local * kMegaRowsPerTile + k * 8 + warp;
+          if (row < op.rows) {
+            if (kind == kMegaNormFwd) avgl1norm_row<false, true>(op, row, g, lane);
+            else avgl1norm_row<true, true>(op, row, g, lane);
           }
         }
         break;
       }
       case kMegaPrep:
-        if (tid == 0 && g == 0) prep_step_body(desc.prep.st, desc.prep.adam, desc.prep.hyper, desc.prep.nopt, desc.prep.step_mask, desc.prep.ring);
+        if (tid == 0 && g == 0) prep_step_body(D.prep.st, D.prep.adam, D.prep.hyper, D.prep.nopt, D.prep.step_mask, D.prep.ring);
         break;
-      case kMegaGauss: gauss_fill_pair(desc.gauss, g, (long long)tl.t_local * kMegaGaussPairs + tid); break;
+      case kMegaGauss: gauss_fill_pair(D.gauss[di], g, (long long)t_local * kMegaGaussPairs + tid); break;
       default: break;
     }
     MEGA_TRACE(2)
-    __threadfence();
+    // publish: the barrier orders every thread's stores before thread 0's device-scope fence, which is cumulative
     __syncthreads();
     if (tid == 0) {
       __threadfence();
@@ -189,9 +214,11 @@ __global__ void __launch_bounds__(kGemmThreads, 2) mega_kernel(const MegaArgs a)
     }
     MEGA_TRACE(3)
 #ifdef B200RL_PROBE
-    if (tid == 0 && a.pad < kMegaTracePrograms && t < kMegaTraceTiles) g_mega_trace[a.pad][t][4] = ((unsigned long long)tl.kind << 32) | ((unsigned long long)tl.desc << 12) | mega_smid();
+    if (tid == 0 && a.pad < kMegaTracePrograms && t < kMegaTraceTiles) g_mega_trace[a.pad][t][4] = ((unsigned long long)kind << 32) | ((unsigned long long)tl.desc << 12) | mega_smid();
 #endif
+    __syncthreads();  // (cur[buf] and the pipeline memory are free; next_v / cur[buf ^ 1] were written before the barrier above)
     v = next_v;
+    buf ^= 1;
   }
   // the last CTA to leave re-arms the control block for the next launch
   if (tid == 0) {
@@ -257,11 +284,13 @@ struct MegaHostNode {
 };
 
 struct MegaProgram {
-  std::vector<MegaDesc> descs;
+  std::vector<MegaDesc> descs;      // one per node, in recording order
+  std::vector<int> desc_kind_index;  // index of that node inside the table array of its kind
   std::vector<MegaHostTile> tiles;
   std::vector<MegaHostNode> nodes;
   // device copies
   MegaArgs args;
+  std::unique_ptr<MegaDescTable> table;
   int grid = 0;
   bool built = false;
   int max_depth = 0;
@@ -509,26 +538,53 @@ struct MegaProgram {
       o.signal = N.flag0 + T.group;
       o.signal2 = N.ngroups > 1 ? N.flag0 + N.ngroups : -1;
       o.wait_first = (int)dw.size();
+      int nw = 0;
       for (auto& w : waits[t]) {
         const MegaHostNode& Q = nodes[w.first];
         MegaWait mw;
         if (w.second == -1) { mw.flag = Q.flag0 + Q.ngroups; mw.need = (unsigned)Q.ntiles; }
         else { mw.flag = Q.flag0 + w.second; mw.need = (unsigned)Q.group_size[w.second]; }
-        dw.push_back(mw);
+        if (nw < kMegaInlineWaits) o.w[nw] = mw;
+        else dw.push_back(mw);
+        ++nw;
       }
-      o.nwait = (int)dw.size() - o.wait_first;
+      o.nwait = nw;
     }
     if (dw.empty()) dw.push_back(MegaWait{0, 0});
-    MegaTile* d_tiles; MegaWait* d_waits; MegaDesc* d_descs; unsigned* d_flags; unsigned* d_ctrl;
+    table = std::make_unique<MegaDescTable>();
+    memset(table.get(), 0, sizeof(MegaDescTable));
+    {
+      // node -> kind from its first tile; place every descriptor in the array of its kind
+      std::vector<int> node_kind(descs.size(), -1);
+      for (int t = 0; t < nt; ++t) node_kind[tile_desc[t]] = tiles[t].kind;
+      desc_kind_index.assign(descs.size(), 0);
+      int ng = 0, nr = 0, ngs = 0, np = 0;
+      for (size_t i = 0; i < descs.size(); ++i) {
+        const int k = node_kind[i];
+        if (k <= kMegaWgrad) {
+          B200_REQUIRE(ng < kMegaMaxGemm, "mega: too many GEMM nodes for one launch (the descriptor table travels in kernel parameters)");
+          table->gemm[ng] = descs[i].gemm; desc_kind_index[i] = ng++;
+        } else if (k == kMegaNormFwd || k == kMegaNormBwd) {
+          B200_REQUIRE(nr < kMegaMaxRows, "mega: too many row-op nodes for one launch");
+          table->rows[nr] = descs[i].rows; desc_kind_index[i] = nr++;
+        } else if (k == kMegaPrep) {
+          B200_REQUIRE(np < 1, "mega: one counter-preparation node per launch");
+          table->prep = descs[i].prep; desc_kind_index[i] = np++;
+        } else {
+          B200_REQUIRE(ngs < 2, "mega: at most two noise nodes per launch");
+          table->gauss[ngs] = descs[i].gauss; desc_kind_index[i] = ngs++;
+        }
+      }
+    }
+    for (int pos = 0; pos < nt; ++pos) dt[pos].desc = desc_kind_index[dt[pos].desc];
+    MegaTile* d_tiles; MegaWait* d_waits; unsigned* d_flags; unsigned* d_ctrl;
     B200_TRY(arena->alloc(&d_tiles, dt.size()));
     B200_TRY(arena->alloc(&d_waits, dw.size()));
-    B200_TRY(arena->alloc(&d_descs, descs.size()));
     B200_TRY(arena->alloc(&d_flags, (size_t)groups * nflags));
     B200_TRY(arena->alloc(&d_ctrl, 8));
     B200_CHECK_CUDA(cudaMemcpy(d_tiles, dt.data(), dt.size() * sizeof(MegaTile), cudaMemcpyHostToDevice));
     B200_CHECK_CUDA(cudaMemcpy(d_waits, dw.data(), dw.size() * sizeof(MegaWait), cudaMemcpyHostToDevice));
-    B200_CHECK_CUDA(cudaMemcpy(d_descs, descs.data(), descs.size() * sizeof(MegaDesc), cudaMemcpyHostToDevice));
-    args.tiles = d_tiles; args.waits = d_waits; args.descs = d_descs; args.flags = d_flags; args.ctrl = d_ctrl;
+    args.tiles = d_tiles; args.waits = d_waits; args.flags = d_flags; args.ctrl = d_ctrl;
     static int program_counter = 0;
     args.ntiles = nt; args.nflags = nflags; args.groups = groups; args.pad = program_counter++;  // (profiling builds: trace slot)
     grid = std::min(nt * groups, 2 * n_sm);
@@ -547,7 +603,7 @@ struct MegaProgram {
       B200_CHECK_CUDA(cudaFuncSetAttribute(mega_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeBytes));
       attr = true;
     }
-    B200_LAUNCH(mega_kernel<false>, dim3((unsigned)grid), dim3(kGemmThreads), (size_t)kPipeBytes, stream, args);
+    B200_LAUNCH(mega_kernel<false>, dim3((unsigned)grid), dim3(kGemmThreads), (size_t)kPipeBytes, stream, args, *table);
     B200_CHECK_LAUNCH();
     return kOk;
   }
