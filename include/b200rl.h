@@ -146,6 +146,10 @@ int b200rl_agent_destroy(b200rl_agent* h);
 int b200rl_agent_net_count(const b200rl_agent* h);
 int b200rl_agent_net_info(const b200rl_agent* h, int net, int64_t* numel, int* nlayers);
 int b200rl_agent_layer_info(const b200rl_agent* h, int net, int layer, int64_t* w_off, int64_t* b_off, int* out_dim, int* in_dim, int* ld);
+/* A critic's first layer consumes cat[state, action] (sale.py:114, mlp.py:86-88): its weight rows hold the state columns,
+ * zero padding up to the next multiple of 4 floats, then the action columns.  *split = number of state columns when the
+ * layer is laid out that way (logical column c >= split lives at c + round_up(split, 4) - split), 0 for a dense row. */
+int b200rl_agent_layer_split(const b200rl_agent* h, int net, int layer, int* split);
 /* group = -1 addresses every stacked seed at once: [groups][numel] contiguous (population checkpoints: one copy per
  * tensor kind instead of one per seed); the TD7 value-range calls take group = -1 the same way ([groups][4]). */
 int b200rl_agent_read(b200rl_agent* h, int net, int which, int group, float* out_host, void* stream);
@@ -163,6 +167,8 @@ int b200rl_agent_set_rng(b200rl_agent* h, uint64_t seed);
 /* fixed device input buffers of the engine ([groups] x {ss[2B][S], action[B][A], reward[B], notdone[B]});
  * group_stride is in floats.  replay.sample can write here directly (zero-copy train_ops). */
 int b200rl_agent_io(b200rl_agent* h, float** ss_dev, float** action_dev, float** reward_dev, float** notdone_dev, int64_t* group_stride);
+/* row strides (floats) of the ss and action buffers above: widths rounded up to 4 floats, zero padding */
+int b200rl_agent_io_ld(b200rl_agent* h, int* ld_state, int* ld_action);
 /* lap.py:45-64 / simple.py sample(batch) straight into the engine's input buffers (what b200rl_agent_update_n does per
  * step); the tensors returned by the Python sample() alias these buffers, so train_ops needs no staging copy */
 int b200rl_replay_sample_to_agent(b200rl_replay* h, b200rl_agent* agent, int batch, const float* u_dev, void* stream);

@@ -111,6 +111,8 @@ SIGNATURES = {
     "b200rl_td7_value_range": (C.c_int, [c_vp, C.c_int, c_vp, c_vp]),
     "b200rl_td7_set_value_range": (C.c_int, [c_vp, C.c_int, c_vp, c_vp]),
     "b200rl_agent_set_rng": (C.c_int, [c_vp, C.c_uint64]),
+    "b200rl_agent_layer_split": (C.c_int, [c_vp, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "b200rl_agent_io_ld": (C.c_int, [c_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "b200rl_agent_io": (C.c_int, [c_vp, C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp), c_i64p]),
     "b200rl_replay_sample_to_agent": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_vp]),
     "b200rl_agent_stage_batch": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

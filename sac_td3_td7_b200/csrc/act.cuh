@@ -11,6 +11,9 @@
 // through distributed shared memory, and one cluster barrier separates the layers.  The observation may live in
 // pinned host memory (read over the bus by the kernel itself) and the action may be written to a pinned host mailbox
 // followed by a sequence tag, so a host-to-host call is: memcpy into the slot, one launch, poll the tag.
+// Weights do not depend on the observation: every CTA requests its slice of ALL later layers (cp.async into ~165 KB of
+// shared memory) before the first phase, so the six dependent phases pay one L2 round trip between them instead of one
+// each (TD7: 14.4 -> see profiles/README.md); only the first phase, which needs its weights at once, reads them directly.
 #pragma once
 #include "gemm.cuh"
 #include "ops.cuh"
@@ -33,6 +36,8 @@ struct ActArgs {
   ActLayer L[7];  // TD7: zs1 zs2 zs3 l0 l1 l2 l3;  MLP: mlp.0 mlp.2 mlp.4
   const float* obs; long long obs_gs;
   float* out; long long out_gs;
+  int pre_off[7];  // float offset (from the prefetch area) of this CTA's slice of layer l, -1: read from global memory
+  int pre_total;   // floats of the prefetch area (0: no prefetch)
   unsigned* done;                    // device counter of finished CTAs (tag only)
   volatile unsigned long long* tag;  // written with tag_value once every seed's action is in `out` (null: none)
   unsigned long long tag_value;
@@ -51,8 +56,9 @@ __device__ __forceinline__ void st_cluster_f32(float* local, unsigned rank, floa
 // result goes into dst[j] of EVERY CTA of the cluster; gout != null: straight to global memory.  A second layer L2r
 // (same input, same output count: zs1 and l0 both read the observation) rides along so that all weight loads of the
 // phase are in flight together.
+// Wsm != null: this CTA's rows [j_lo, j_hi) of W have been prefetched to shared memory (row stride ld).
 __device__ __forceinline__ void act_matvec(const ActLayer& Lr, int g, const float* xa, int na, const float* xb, int nb, int act, float* dst, float* gout, unsigned rank,
-                                           const ActLayer* L2r = nullptr, int act2 = 0, float* dst2 = nullptr) {
+                                           const ActLayer* L2r = nullptr, int act2 = 0, float* dst2 = nullptr, const float* Wsm = nullptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per = (Lr.out + kActCluster - 1) / kActCluster;
   const int j_lo = (int)rank * per, j_hi = min(Lr.out, j_lo + per);
@@ -68,7 +74,7 @@ __device__ __forceinline__ void act_matvec(const ActLayer& Lr, int g, const floa
     const float* wr2[4];
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
-      wr[o] = W + (long long)min(j0 + o, Lr.out - 1) * Lr.ld;
+      wr[o] = Wsm ? Wsm + (long long)(min(j0 + o, j_hi - 1) - j_lo) * Lr.ld : W + (long long)min(j0 + o, Lr.out - 1) * Lr.ld;
       wr2[o] = W2 ? W2 + (long long)min(j0 + o, Lr.out - 1) * L2r->ld : nullptr;
     }
     const int jf = min(j0 + o_fin, Lr.out - 1);
@@ -85,7 +91,7 @@ __device__ __forceinline__ void act_matvec(const ActLayer& Lr, int g, const floa
           const float4 xv = *reinterpret_cast<const float4*>(x + k);
           float4 wv[4], wv2[4];
 #pragma unroll
-          for (int o = 0; o < 4; ++o) wv[o] = __ldg(reinterpret_cast<const float4*>(wr[o] + koff + k));
+          for (int o = 0; o < 4; ++o) wv[o] = Wsm ? *reinterpret_cast<const float4*>(wr[o] + koff + k) : __ldg(reinterpret_cast<const float4*>(wr[o] + koff + k));
           if (W2) {
 #pragma unroll
             for (int o = 0; o < 4; ++o) wv2[o] = __ldg(reinterpret_cast<const float4*>(wr2[o] + koff + k));
@@ -101,7 +107,7 @@ __device__ __forceinline__ void act_matvec(const ActLayer& Lr, int g, const floa
         for (int k = lane; k < n; k += 32) {
           const float xv = x[k];
 #pragma unroll
-          for (int o = 0; o < 4; ++o) acc[o] = fmaf(__ldg(wr[o] + koff + k), xv, acc[o]);
+          for (int o = 0; o < 4; ++o) acc[o] = fmaf(Wsm ? wr[o][koff + k] : __ldg(wr[o] + koff + k), xv, acc[o]);
           if (W2) {
 #pragma unroll
             for (int o = 0; o < 4; ++o) acc2[o] = fmaf(__ldg(wr2[o] + koff + k), xv, acc2[o]);
@@ -143,6 +149,20 @@ __device__ __forceinline__ void act_norm(float* x, int n, float* red) {
   __syncthreads();
 }
 
+// request this CTA's rows of layer l (one contiguous block of the packed blob) into the prefetch area; one commit group
+__device__ __forceinline__ void act_prefetch(const ActArgs& a, int l, int g, unsigned rank, float* wb) {
+  if (a.pre_off[l] >= 0) {
+    const ActLayer& Lr = a.L[l];
+    const int per = (Lr.out + kActCluster - 1) / kActCluster;
+    const int j_lo = (int)rank * per, j_hi = min(Lr.out, j_lo + per);
+    const int n = max(0, j_hi - j_lo) * Lr.ld;  // (ld is a multiple of 4 floats and the blob is 16-byte aligned)
+    const float* src = Lr.W + (long long)g * Lr.gs + (long long)j_lo * Lr.ld;
+    float* dst = wb + a.pre_off[l];
+    for (int k = threadIdx.x * 4; k < n; k += kActThreads * 4) cp_async16(dst + k, src + k);
+  }
+  cp_async_commit();
+}
+
 // a single agent's observation travels BY VALUE in the kernel parameters (<= 4 KB): no pinned slot, no read over the bus
 constexpr int kActInlineObs = 1024;
 struct ActObs { float v[kActInlineObs]; };
@@ -158,6 +178,9 @@ __global__ void __cluster_dims__(kActCluster, 1, 1) __launch_bounds__(kActThread
   float* v1 = v0 + a.vmax;
   float* v2 = v1 + a.vmax;
   float* v3 = v2 + a.vmax;
+  float* wb = v3 + a.vmax;                     // prefetched weight slices
+  auto wsm = [&](int l) -> const float* { return a.pre_off[l] >= 0 ? wb + a.pre_off[l] : nullptr; };
+  act_prefetch(a, 1, g, rank, wb);  // the second phase's weights first: they are needed soonest
   if (INLINE_OBS) {
     for (int k = threadIdx.x; k < a.S; k += kActThreads) xo[k] = ob.v[k];
   } else {
@@ -175,24 +198,33 @@ __global__ void __cluster_dims__(kActCluster, 1, 1) __launch_bounds__(kActThread
       act_matvec(a.L[0], g, xo, a.S, nullptr, 0, kActElu, v0, nullptr, rank);
       act_matvec(a.L[3], g, xo, a.S, nullptr, 0, kActNone, v1, nullptr, rank);
     }
+    act_prefetch(a, 2, g, rank, wb); act_prefetch(a, 4, g, rank, wb); act_prefetch(a, 5, g, rank, wb); act_prefetch(a, 6, g, rank, wb);
+    cp_async_wait<4>();  // (this thread's part of layer 1; the cluster barrier covers everybody's)
     cluster_arrive(); cluster_wait();
-    act_matvec(a.L[1], g, v0, a.H, nullptr, 0, kActElu, v2, nullptr, rank);   // h2 = elu(zs2 h1)
+    act_matvec(a.L[1], g, v0, a.H, nullptr, 0, kActElu, v2, nullptr, rank, nullptr, 0, nullptr, wsm(1));   // h2 = elu(zs2 h1)
     act_norm(v1, a.H, red);                                                   // p0n (local copy; nobody writes v1 any more)
+    cp_async_wait<3>();
     cluster_arrive(); cluster_wait();
-    act_matvec(a.L[2], g, v2, a.H, nullptr, 0, kActNone, v3, nullptr, rank);  // u3 = zs3 h2
+    act_matvec(a.L[2], g, v2, a.H, nullptr, 0, kActNone, v3, nullptr, rank, nullptr, 0, nullptr, wsm(2));  // u3 = zs3 h2
+    cp_async_wait<2>();
     cluster_arrive(); cluster_wait();
     act_norm(v3, a.Z, red);                                                   // zs
-    act_matvec(a.L[4], g, v1, a.H, v3, a.Z, kActRelu, v0, nullptr, rank);     // a1 = relu(l1 [p0n, zs])
+    act_matvec(a.L[4], g, v1, a.H, v3, a.Z, kActRelu, v0, nullptr, rank, nullptr, 0, nullptr, wsm(4));     // a1 = relu(l1 [p0n, zs])
+    cp_async_wait<1>();
     cluster_arrive(); cluster_wait();
-    act_matvec(a.L[5], g, v0, a.H, nullptr, 0, kActRelu, v2, nullptr, rank);  // a2 = relu(l2 a1)
+    act_matvec(a.L[5], g, v0, a.H, nullptr, 0, kActRelu, v2, nullptr, rank, nullptr, 0, nullptr, wsm(5));  // a2 = relu(l2 a1)
+    cp_async_wait<0>();
     cluster_arrive(); cluster_wait();
-    act_matvec(a.L[6], g, v2, a.H, nullptr, 0, kActTanh, nullptr, out, rank);  // a = tanh(l3 a2)
+    act_matvec(a.L[6], g, v2, a.H, nullptr, 0, kActTanh, nullptr, out, rank, nullptr, 0, nullptr, wsm(6));  // a = tanh(l3 a2)
   } else {
     act_matvec(a.L[0], g, xo, a.S, nullptr, 0, kActRelu, v0, nullptr, rank);
+    act_prefetch(a, 2, g, rank, wb);
+    cp_async_wait<1>();
     cluster_arrive(); cluster_wait();
-    act_matvec(a.L[1], g, v0, a.H, nullptr, 0, kActRelu, v1, nullptr, rank);
+    act_matvec(a.L[1], g, v0, a.H, nullptr, 0, kActRelu, v1, nullptr, rank, nullptr, 0, nullptr, wsm(1));
+    cp_async_wait<0>();
     cluster_arrive(); cluster_wait();
-    act_matvec(a.L[2], g, v1, a.H, nullptr, 0, a.kind == 1 ? kActTanh : kActNone, nullptr, out, rank);
+    act_matvec(a.L[2], g, v1, a.H, nullptr, 0, a.kind == 1 ? kActTanh : kActNone, nullptr, out, rank, nullptr, 0, nullptr, wsm(2));
   }
   if (a.tag && a.total_ctas == (unsigned)kActCluster) {  // one seed: the cluster barrier orders the eight CTAs' stores, CTA 0 posts the tag
     __syncthreads();

@@ -33,15 +33,20 @@ struct StageArgs {
   const float* state; const float* action; const float* reward; const float* next_state; const float* done;
   float* ss; float* act; float* rew; float* nd;
   int B, S, A;
+  int ld_s, ld_a;  // leading dimensions of the engine's state / action buffers
 };
 __global__ void __launch_bounds__(256) stage_batch_kernel(StageArgs a) {
   B200_PDL_PROLOGUE();
   const int nS = a.B * a.S, nA = a.B * a.A;
   const int total = 2 * nS + nA + 2 * a.B;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    if (i < nS) a.ss[i] = a.state[i];
-    else if (i < 2 * nS) a.ss[i] = a.next_state[i - nS];
-    else if (i < 2 * nS + nA) a.act[i - 2 * nS] = a.action[i - 2 * nS];
+    if (i < 2 * nS) {
+      const int r = i / a.S, c = i - r * a.S;  // rows 0..B-1: state, B..2B-1: next_state
+      a.ss[(long long)r * a.ld_s + c] = (r < a.B) ? a.state[i] : a.next_state[i - nS];
+    } else if (i < 2 * nS + nA) {
+      const int k = i - 2 * nS, r = k / a.A, c = k - r * a.A;
+      a.act[(long long)r * a.ld_a + c] = a.action[k];
+    }
     else if (i < 2 * nS + nA + a.B) a.rew[i - 2 * nS - nA] = a.reward[i - 2 * nS - nA];
     else a.nd[i - 2 * nS - nA - a.B] = a.done[i - 2 * nS - nA - a.B];
   }
@@ -92,12 +97,14 @@ struct AgentBase {
     if (h_mail) cudaFreeHost(h_mail);
   }
 
-  Mat alloc_act(int rows, int cols) {
+  // pad4: rows start every round_up(cols, 4) floats (the arena is zero-filled and nothing writes the padding), which
+  // makes observation- and action-wide activations 16-byte aligned operands (TMA, 128-bit loads)
+  Mat alloc_act(int rows, int cols, bool pad4 = false) {
     Mat m;
-    m.rows = rows; m.cols = cols; m.ld = cols;
+    m.rows = rows; m.cols = cols; m.ld = pad4 ? (int)round_up(cols, 4) : cols;
     m.p = act_base ? act_base + act_cursor : nullptr;
     m.gs = act_stride;
-    act_cursor += round_up((long long)rows * cols, 4);
+    act_cursor += round_up((long long)rows * m.ld, 4);
     return m;
   }
 
@@ -202,7 +209,7 @@ struct AgentBase {
     const long long o = (long long)group * act_stride;
     a.state = state; a.action = action; a.reward = reward; a.next_state = next_state; a.done = done;
     a.ss = ss.p + o; a.act = act_in.p + o; a.rew = rew.p + o; a.nd = nd.p + o;
-    a.B = B; a.S = S; a.A = A;
+    a.B = B; a.S = S; a.A = A; a.ld_s = ss.ld; a.ld_a = act_in.ld;
     B200_LAUNCH(stage_batch_kernel, dim3(32), dim3(256), 0, exec, a);
     B200_CHECK_LAUNCH();
     return kOk;
@@ -210,9 +217,9 @@ struct AgentBase {
 
   Replay::Outputs replay_outputs() const {
     Replay::Outputs o;
-    o.state = ss.p; o.ld_state = S; o.state_gs = act_stride;
-    o.next_state = ss.p + (long long)B * S; o.ld_next = S; o.next_gs = act_stride;
-    o.action = act_in.p; o.ld_action = A; o.action_gs = act_stride;
+    o.state = ss.p; o.ld_state = ss.ld; o.state_gs = act_stride;
+    o.next_state = ss.p + (long long)B * ss.ld; o.ld_next = ss.ld; o.next_gs = act_stride;
+    o.action = act_in.p; o.ld_action = act_in.ld; o.action_gs = act_stride;
     o.reward = rew.p; o.reward_gs = act_stride;
     o.done = nd.p; o.done_gs = act_stride;
     return o;

@@ -40,10 +40,10 @@ struct MlpAgent : AgentBase {
 
   void layout_acts() {
     act_cursor = 0;
-    ss = alloc_act(2 * B, S); act_in = alloc_act(B, A); rew = alloc_act(B, 1); nd = alloc_act(B, 1);
+    ss = alloc_act(2 * B, S, true); act_in = alloc_act(B, A, true); rew = alloc_act(B, 1); nd = alloc_act(B, 1);
     noise = alloc_act(B, A); noise2 = alloc_act(B, A);
-    h1 = alloc_act(B, H); h2 = alloc_act(B, H); pout_n = alloc_act(B, Aout); a_next = alloc_act(B, A); logp_n = alloc_act(B, 1);
-    g1 = alloc_act(B, H); g2 = alloc_act(B, H); pout = alloc_act(B, Aout); a_pi = alloc_act(B, A); logp = alloc_act(B, 1);
+    h1 = alloc_act(B, H); h2 = alloc_act(B, H); pout_n = alloc_act(B, Aout); a_next = alloc_act(B, A, true); logp_n = alloc_act(B, 1);
+    g1 = alloc_act(B, H); g2 = alloc_act(B, H); pout = alloc_act(B, Aout); a_pi = alloc_act(B, A, true); logp = alloc_act(B, 1);
     dlogp = alloc_act(B, 1); d_api = alloc_act(B, A); d_pout = alloc_act(B, Aout); d_g2 = alloc_act(B, H); d_g1 = alloc_act(B, H);
     for (int k = 0; k < 2; ++k) {
       c1[k] = alloc_act(B, H); c2[k] = alloc_act(B, H); qv[k] = alloc_act(B, 1);
@@ -72,8 +72,8 @@ struct MlpAgent : AgentBase {
     B200_TRY(alloc_net(&pol, make_layout(kNetMlp, S, A, H, 0, S, Aout), true, d_adam + 0));
     keep_grads = kg;
     for (int k = 0; k < 2; ++k) {
-      B200_TRY(alloc_net(&q[k], make_layout(kNetMlp, S, A, H, 0, S + A, 1), true, d_adam + 1));
-      B200_TRY(alloc_net(&qt[k], make_layout(kNetMlp, S, A, H, 0, S + A, 1), false, nullptr));
+      B200_TRY(alloc_net(&q[k], make_layout(kNetMlp, S, A, H, 0, S + A, 1, S), true, d_adam + 1));
+      B200_TRY(alloc_net(&qt[k], make_layout(kNetMlp, S, A, H, 0, S + A, 1, S), false, nullptr));
     }
     if (sac) {
       B200_TRY(arena.alloc(&la_p, (size_t)G)); B200_TRY(arena.alloc(&la_m, (size_t)G));

@@ -53,13 +53,13 @@ struct TD7Agent : AgentBase {
   void layout_acts() {
     act_cursor = 0;
     const int B2 = 2 * B;
-    ss = alloc_act(B2, S); act_in = alloc_act(B, A); rew = alloc_act(B, 1); nd = alloc_act(B, 1); noise = alloc_act(B, A);
+    ss = alloc_act(B2, S, true); act_in = alloc_act(B, A, true); rew = alloc_act(B, 1); nd = alloc_act(B, 1); noise = alloc_act(B, A);
     e_h1 = alloc_act(B2, H); e_h2 = alloc_act(B2, H); e_u3 = alloc_act(B2, Z); e_z = alloc_act(B2, Z);
     e_g1 = alloc_act(B, H); e_g2 = alloc_act(B, H); e_zsa = alloc_act(B, Z); d_zsa = alloc_act(B, Z);
     d_g2 = alloc_act(B, H); d_g1 = alloc_act(B, H); d_z = alloc_act(B, Z); d_u3 = alloc_act(B, Z); d_h2 = alloc_act(B, H); d_h1 = alloc_act(B, H);
     t1 = alloc_act(B, H); t2 = alloc_act(B, H); tu3 = alloc_act(B, Z); zs_t = alloc_act(B, Z);
     f1 = alloc_act(B, H); f2 = alloc_act(B, H); fu3 = alloc_act(B, Z); zs_f = alloc_act(B, Z);
-    pa0 = alloc_act(B, H); pa0n = alloc_act(B, H); p1 = alloc_act(B, H); p2 = alloc_act(B, H); a_next = alloc_act(B, A);
+    pa0 = alloc_act(B, H); pa0n = alloc_act(B, H); p1 = alloc_act(B, H); p2 = alloc_act(B, H); a_next = alloc_act(B, A, true);
     fa1 = alloc_act(B, H); fa2 = alloc_act(B, H); zsa_f = alloc_act(B, Z); ta1 = alloc_act(B, H); ta2 = alloc_act(B, H); zsa_t = alloc_act(B, Z);
     for (int k = 0; k < 2; ++k) {
       tq0[k] = alloc_act(B, H); tq0n[k] = alloc_act(B, H); tqa[k] = alloc_act(B, H); tqb[k] = alloc_act(B, H); qtv[k] = alloc_act(B, 1);
@@ -69,7 +69,7 @@ struct TD7Agent : AgentBase {
       dqa[k] = alloc_act(B, 1);
       d_aqb[k] = alloc_act(B, H); d_aqa[k] = alloc_act(B, H); d_aq0n[k] = alloc_act(B, H); d_aq0[k] = alloc_act(B, H);
     }
-    pb0 = alloc_act(B, H); pb0n = alloc_act(B, H); pp1 = alloc_act(B, H); pp2 = alloc_act(B, H); a_pi = alloc_act(B, A);
+    pb0 = alloc_act(B, H); pb0n = alloc_act(B, H); pp1 = alloc_act(B, H); pp2 = alloc_act(B, H); a_pi = alloc_act(B, A, true);
     pa1 = alloc_act(B, H); pa2 = alloc_act(B, H); zsa_pi = alloc_act(B, Z);
     d_zsa_pi = alloc_act(B, Z); d_pa2 = alloc_act(B, H); d_pa1 = alloc_act(B, H); d_api = alloc_act(B, A);
     d_pp2 = alloc_act(B, H); d_pp1 = alloc_act(B, H); d_pb0n = alloc_act(B, H); d_pb0 = alloc_act(B, H);

@@ -314,7 +314,26 @@ static int build_act_path(b200rl_agent* h) {
     for (int l = 0; l < 3; ++l) aa.L[l] = layer(m.pol, l);
   }
   aa.total_ctas = (unsigned)(a.G * kActCluster);
-  h->act_smem = (int)((round_up(S, 4) + 4ll * aa.vmax) * sizeof(float));
+  // weight slices prefetched by every CTA (act.cuh): all layers behind the first phase, if they fit beside the vectors
+  {
+    const int nl = h->td7 ? 7 : 3;
+    long long tot = 0;
+    for (int l = 0; l < 7; ++l) aa.pre_off[l] = -1;
+    for (int l = 1; l < nl; ++l) {
+      if (h->td7 && l == 3) continue;  // l0 reads the observation in the first phase, beside zs1
+      aa.pre_off[l] = (int)tot;
+      tot += (long long)ceil_div(aa.L[l].out, kActCluster) * aa.L[l].ld;
+    }
+    static const bool pre = [] { const char* e = getenv("B200RL_ACT_PREFETCH"); return e ? atoi(e) != 0 : true; }();
+    // (only while every cluster of the launch is resident at once: with hundreds of stacked seeds the kernel runs in
+    // waves, where many small CTAs per SM hide the weight reads better than one CTA holding 165 KB)
+    if (!pre || a.G * kActCluster > 148 || (round_up(S, 4) + 4ll * aa.vmax + tot) * (long long)sizeof(float) > 200 * 1024) {
+      for (int l = 0; l < 7; ++l) aa.pre_off[l] = -1;
+      tot = 0;
+    }
+    aa.pre_total = (int)tot;
+  }
+  h->act_smem = (int)((round_up(S, 4) + 4ll * aa.vmax + aa.pre_total) * sizeof(float));
   B200_REQUIRE(h->act_smem <= 200 * 1024, "acting path: observation / hidden sizes too large for the fused kernel");
 #ifndef B200_EMU
   B200_TRY(a.arena.alloc(&h->d_done, 1));
@@ -429,6 +448,14 @@ int b200rl_agent_layer_info(const b200rl_agent* h, int net, int layer, int64_t* 
   if (out_dim) *out_dim = L[layer].out;
   if (in_dim) *in_dim = L[layer].in;
   if (ld) *ld = L[layer].ld;
+  return kOk;
+}
+
+int b200rl_agent_layer_split(const b200rl_agent* h, int net, int layer, int* split) {
+  B200_REQUIRE(h && split && net >= 0 && net < (int)h->nets.size(), "bad handle, net id or null argument");
+  const auto& L = h->nets[net]->L.layers;
+  B200_REQUIRE(layer >= 0 && layer < (int)L.size(), "bad layer");
+  *split = L[layer].split;
   return kOk;
 }
 
@@ -561,6 +588,12 @@ int b200rl_agent_io(b200rl_agent* h, float** ss_dev, float** action_dev, float**
   if (reward_dev) *reward_dev = a.rew.p;
   if (notdone_dev) *notdone_dev = a.nd.p;
   if (group_stride) *group_stride = a.act_stride;
+  return kOk;
+}
+int b200rl_agent_io_ld(b200rl_agent* h, int* ld_state, int* ld_action) {
+  B200_REQUIRE(h, "null argument");
+  if (ld_state) *ld_state = h->base->ss.ld;
+  if (ld_action) *ld_action = h->base->act_in.ld;
   return kOk;
 }
 int b200rl_replay_sample_to_agent(b200rl_replay* replay, b200rl_agent* h, int batch, const float* u_dev, void* stream) {
@@ -732,7 +765,8 @@ int b200rl_agent_debug_read(b200rl_agent* h, int which, int group, float* out_ho
     B200_REQUIRE(which >= 0 && which < (t.sac ? 7 : 6), "which must be 0..5 (SAC: 0..6)");
     m = tab[which];
   }
-  B200_CHECK_CUDA(cudaMemcpyAsync(out_host, m->p + (long long)group * m->gs, (size_t)m->rows * m->cols * sizeof(float), cudaMemcpyDeviceToHost, as_stream(stream)));
+  B200_CHECK_CUDA(cudaMemcpy2DAsync(out_host, (size_t)m->cols * sizeof(float), m->p + (long long)group * m->gs, (size_t)m->ld * sizeof(float), (size_t)m->cols * sizeof(float),
+                                    (size_t)m->rows, cudaMemcpyDeviceToHost, as_stream(stream)));
   B200_CHECK_CUDA(cudaStreamSynchronize(as_stream(stream)));
   return kOk;
 }

@@ -957,20 +957,5 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const __grid_constant__ 
   }
 }
 
-// ----------------------------------------------------------------------------- host side
-// A launch table: problems are appended on the host once, then replayed (the struct is passed by value
-// as the kernel parameter; nothing lives in device memory).
-struct GemmTable {
-  FfmaLaunch launch;      // problems run by the FFMA kernel
-  BiasLaunch launch_bias; // bias gradients of stacked seeds (tensor-core path only)
-  GemmLaunch launch_tc;   // problems run by the tcgen05 kernel (stacked seeds; gemm_tc.cuh)
-  GemmLaunch launch_ws;   // ... of which the TMA-addressable ones, run by the persistent warp-specialised variant
-  int nprob = 0;
-  int total_tiles = 0;    // FFMA tiles (32 x 32)
-  int tc_tiles = 0;       // tcgen05 tiles (128 rows x N)
-  int mode = kFwd;
-  int groups = 1;
-  bool debug_print = false;
-};
 
 }  // namespace b200rl

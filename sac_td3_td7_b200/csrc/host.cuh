@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "gemm.cuh"
 #include "gemm_tc.cuh"
+#include "narrow.cuh"
 #include "ops.cuh"
 
 namespace b200rl {
@@ -128,6 +129,32 @@ inline bool use_tensor_cores(int groups) {
 #endif
 }
 
+// ----------------------------------------------------------------------------- host side
+// A launch table: problems are appended on the host once, then replayed (the struct is passed by value
+// as the kernel parameter; nothing lives in device memory).
+struct GemmTable {
+  FfmaLaunch launch;      // problems run by the FFMA kernel
+  BiasLaunch launch_bias; // bias gradients of stacked seeds (tensor-core path only)
+  GemmLaunch launch_tc;   // problems run by the tcgen05 kernel (stacked seeds; gemm_tc.cuh)
+  GemmLaunch launch_ws;   // ... of which the TMA-addressable ones, run by the persistent warp-specialised variant
+  NarrowWgradLaunch launch_nw;  // narrow.cuh: weight gradients a few input columns wide (+ their layer's bias gradient)
+  NarrowRowsLaunch launch_nr;   //             forward / dgrad problems with at most 8 output columns
+  Rank1Launch launch_r1;        //             dgrad through a one-output layer
+  int nprob = 0;
+  int total_tiles = 0;    // FFMA tiles (32 x 32)
+  int tc_tiles = 0;       // tcgen05 tiles (128 rows x N)
+  int mode = kFwd;
+  int groups = 1;
+  bool debug_print = false;
+};
+
+// Narrow problems of a stacked-seed update (narrow.cuh): on wherever the tensor cores are (default), B200RL_NARROW=0
+// keeps them on the FFMA / tcgen05 kernels (A/B), B200RL_NARROW=1 forces them for any seed count (emulation tests).
+inline bool use_narrow(int groups) {
+  static const int env = [] { const char* e = getenv("B200RL_NARROW"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+  return env >= 0 ? env != 0 : use_tensor_cores(groups);
+}
+
 // The small-tile kernel's product loop: fp32 FFMA (default), or error-compensated 3xTF32 on the warp-level tensor-core
 // path (B200RL_MMA=1 / b200rl_set_mma).  Measured on B200: HMMA.1688.F32.TF32 issues at about the FFMA MAC rate per SM
 // (the legacy mma.sync path is not the fast tensor path on Blackwell), so with three MMAs per product the chunk loop is
@@ -197,18 +224,87 @@ inline bool use_tma() {
 
 inline int gemm_table_upload(GemmTable* t, int mode, std::vector<GemmProblem>& probs, DeviceArena* arena, int groups = 1, int force_splitk = 0) {
   B200_REQUIRE((int)probs.size() <= kMaxProblems, "too many problems in one gemm launch");
-  std::vector<GemmProblem> ff, tc, bias;
-  const bool want_tc = use_tensor_cores(groups);
+  std::vector<GemmProblem> ff, tc, bias, nw, nr, r1;
+  const bool want_tc = use_tensor_cores(groups), want_narrow = use_narrow(groups);
   for (auto& p : probs) {
     B200_REQUIRE(p.nseg >= 1 && p.nseg <= 3, "gemm problem needs 1..3 segments");
     B200_REQUIRE(p.I > 0 && p.J > 0, "gemm problem with empty output");
+    if (want_narrow && rank1_eligible(p, mode)) { r1.push_back(p); continue; }
 #ifndef B200_EMU
     if (want_tc && tc_eligible(p)) { tc.push_back(p); continue; }
-    if (want_tc && mode == kWgrad && p.nseg == 1 && p.seg[0].b_ones && p.J == 1) { bias.push_back(p); continue; }
 #endif
+    if (want_narrow && mode == kWgrad && narrow_wgrad_eligible(p)) { nw.push_back(p); continue; }
+    if (want_narrow && narrow_rows_eligible(p, mode)) { nr.push_back(p); continue; }
+    if ((want_tc || want_narrow) && mode == kWgrad && p.nseg == 1 && p.seg[0].b_ones && p.J == 1) { bias.push_back(p); continue; }
     ff.push_back(p);
   }
   (void)want_tc;
+  // ---- narrow problems (narrow.cuh)
+  memset(&t->launch_nw, 0, sizeof(t->launch_nw));
+  memset(&t->launch_nr, 0, sizeof(t->launch_nr));
+  memset(&t->launch_r1, 0, sizeof(t->launch_r1));
+  {
+    int units = 0;
+    for (size_t i = 0; i < nw.size(); ++i) {
+      const GemmProblem& p = nw[i];
+      NarrowWgrad& q = t->launch_nw.p[i];
+      q.dZ = p.seg[0].A; q.dz_gs = p.seg[0].a_gs; q.dz_ld = p.seg[0].a_ld; q.rows = p.seg[0].len; q.out = p.I;
+      q.X = p.seg[0].B; q.x_gs = p.seg[0].b_gs; q.x_ld = p.seg[0].b_ld; q.J = p.J;
+      q.C = p.C; q.P = p.P; q.M = p.M; q.V = p.V;
+      q.p_gs = p.P ? p.p_gs : p.c_gs; q.p_ld = p.P ? p.p_ld : p.c_ld;
+      q.adam = p.adam;
+      q.jchunks = ceil_div(p.J, kNwCols);
+      q.unit_begin = units;
+      units += q.jchunks * ceil_div(p.I, kNwThreads);
+    }
+    t->launch_nw.nprob = (int)nw.size();
+    t->launch_nw.total_units = units;
+    if (const char* e = getenv("B200RL_NW_DBG")) t->launch_nw.dbg = atoi(e);
+    // the bias gradient of a layer (column sums of the same dZ) rides with the first narrow problem of that layer
+    std::vector<GemmProblem> bias_left;
+    for (auto& b : bias) {
+      bool folded = false;
+      for (size_t i = 0; i < nw.size() && !folded; ++i) {
+        NarrowWgrad& q = t->launch_nw.p[i];
+        if (q.dZ == b.seg[0].A && q.dz_gs == b.seg[0].a_gs && q.out == b.I && !q.bP && !q.bC && (b.P ? b.p_gs : b.c_gs) == q.p_gs && (!b.P || b.adam == q.adam || !q.P)) {
+          q.bC = b.C; q.bP = b.P; q.bM = b.M; q.bV = b.V;
+          if (!q.adam) q.adam = b.adam;
+          folded = true;
+        }
+      }
+      if (!folded) bias_left.push_back(b);
+    }
+    bias.swap(bias_left);
+    units = 0;
+    for (size_t i = 0; i < nr.size(); ++i) {
+      const GemmProblem& p = nr[i];
+      NarrowRows& q = t->launch_nr.p[i];
+      for (int s = 0; s < 3; ++s) q.seg[s] = p.seg[s];
+      q.nseg = p.nseg; q.I = p.I; q.J = p.J;
+      q.C = p.C; q.c_gs = p.c_gs; q.c_ld = p.c_ld; q.act = p.act;
+      q.bias = p.bias; q.bias_gs = p.bias_gs;
+      q.aux = p.aux; q.aux_gs = p.aux_gs; q.aux_ld = p.aux_ld; q.accumulate = p.accumulate;
+      q.noise_sigma = p.noise_sigma; q.noise_clip = p.noise_clip;
+      q.unit_begin = units;
+      units += ceil_div(p.I, 32);
+    }
+    t->launch_nr.nprob = (int)nr.size();
+    t->launch_nr.total_units = units;
+    long long quads = 0;
+    for (size_t i = 0; i < r1.size(); ++i) {
+      const GemmProblem& p = r1[i];
+      Rank1Problem& q = t->launch_r1.p[i];
+      q.dz = p.seg[0].A; q.dz_gs = p.seg[0].a_gs; q.dz_ld = p.seg[0].a_ld;
+      q.w = p.seg[0].B; q.w_gs = p.seg[0].b_gs;
+      q.aux = p.aux; q.aux_gs = p.aux_gs; q.aux_ld = p.aux_ld; q.act = p.act;
+      q.C = p.C; q.c_gs = p.c_gs; q.c_ld = p.c_ld; q.accumulate = p.accumulate;
+      q.I = p.I; q.J = p.J;
+      q.quad_begin = quads;
+      quads += (long long)p.I * (p.J / 4);
+    }
+    t->launch_r1.nprob = (int)r1.size();
+    t->launch_r1.total_quads = quads;
+  }
   // longest reductions first: their CTAs are scheduled in the first wave and the short problems fill in behind
   std::stable_sort(ff.begin(), ff.end(), [&](const GemmProblem& a, const GemmProblem& b) { return chunks_of(a) > chunks_of(b); });
   std::stable_sort(tc.begin(), tc.end(), [&](const GemmProblem& a, const GemmProblem& b) { return chunks_of(a) > chunks_of(b); });
@@ -255,8 +351,8 @@ inline int gemm_table_upload(GemmTable* t, int mode, std::vector<GemmProblem>& p
   if (getenv("B200RL_DEBUG_TABLES")) {
     int mc = 0;
     for (auto& p : ff) mc = std::max(mc, chunks_of(p));
-    fprintf(stderr, "[b200rl] gemm table %d mode=%d problems=%zu (+%zu tc) tiles=%d groups=%d max_chunks=%d splitk=%d\n", t->launch.tag, mode, ff.size(),
-            tc.size(), tiles, groups, mc, splitk);
+    fprintf(stderr, "[b200rl] gemm table %d mode=%d problems=%zu (+%zu tc, %zu narrow wgrad, %zu narrow rows, %zu rank-1, %zu bias) tiles=%d groups=%d max_chunks=%d splitk=%d\n",
+            t->launch.tag, mode, ff.size(), tc.size(), nw.size(), nr.size(), r1.size(), bias.size(), tiles, groups, mc, splitk);
     t->debug_print = true;
   }
   t->launch_tc.nprob = (int)tc.size();
@@ -368,12 +464,32 @@ inline int gemm_table_launch(const GemmTable& t, int groups, cudaStream_t stream
     B200_CHECK_LAUNCH();
   }
 #endif
-#ifndef B200_EMU
   if (t.launch_bias.nprob > 0) {
     B200_LAUNCH(bias_grad_kernel, dim3((unsigned)t.launch_bias.nprob, (unsigned)groups), dim3(256), 0, stream, t.launch_bias);
     B200_CHECK_LAUNCH();
   }
+  if (t.launch_nw.nprob > 0) {
+#ifndef B200_EMU
+    static bool nw_attr = false;
+    if (!nw_attr) {
+      B200_CHECK_CUDA(cudaFuncSetAttribute(narrow_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNwSmemBytes));
+      nw_attr = true;
+    }
 #endif
+    B200_LAUNCH(narrow_wgrad_kernel, dim3((unsigned)t.launch_nw.total_units, (unsigned)groups), dim3(kNwThreads), (size_t)kNwSmemBytes, stream, t.launch_nw);
+    B200_CHECK_LAUNCH();
+  }
+  if (t.launch_nr.nprob > 0) {
+    dim3 grid((unsigned)t.launch_nr.total_units, (unsigned)groups), block(kNrThreads);
+    if (t.mode == kFwd) { auto k = narrow_rows_kernel<kFwd>; B200_LAUNCH(k, grid, block, 0, stream, t.launch_nr); }
+    else { auto k = narrow_rows_kernel<kDgrad>; B200_LAUNCH(k, grid, block, 0, stream, t.launch_nr); }
+    B200_CHECK_LAUNCH();
+  }
+  if (t.launch_r1.nprob > 0) {
+    const long long blocks = (t.launch_r1.total_quads + 255) / 256;
+    B200_LAUNCH(rank1_dgrad_kernel, dim3((unsigned)std::min<long long>(blocks, 148 * 8), (unsigned)groups), dim3(256), 0, stream, t.launch_r1);
+    B200_CHECK_LAUNCH();
+  }
   if (t.launch.nprob > 0) {
     const int sk = t.launch.splitk;
     dim3 grid((unsigned)(t.total_tiles * sk), (unsigned)groups, 1), block(kGemmThreads, 1, 1);

@@ -32,6 +32,7 @@
 #include <set>
 
 #include "gemm.cuh"
+#include "host.cuh"
 #include "ops.cuh"
 
 namespace b200rl {

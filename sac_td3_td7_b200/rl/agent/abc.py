@@ -23,6 +23,14 @@ AGENT = TypeVar("AGENT", bound="Agent")
 _stream = _lib.current_stream_ptr
 
 
+def _layer_cols(n: int, split: int):
+    """Physical columns of a packed weight row holding the n logical input columns (b200rl_agent_layer_split)."""
+    if not split:
+        return slice(0, n)
+    s4 = (split + 3) // 4 * 4
+    return np.r_[0:split, s4:s4 + n - split]
+
+
 class LazyScalar:
     """A loss value that stays on the device until somebody looks at it.
 
@@ -113,7 +121,9 @@ class Agent(ABC):
         for i in range(nl.value):
             wo, bo, o, n, ld = C.c_int64(), C.c_int64(), C.c_int(), C.c_int(), C.c_int()
             _lib.check(self._lib.b200rl_agent_layer_info(self._h, net, i, C.byref(wo), C.byref(bo), C.byref(o), C.byref(n), C.byref(ld)))
-            out.append((wo.value, bo.value, o.value, n.value, ld.value))
+            sp = C.c_int()
+            _lib.check(self._lib.b200rl_agent_layer_split(self._h, net, i, C.byref(sp)))
+            out.append((wo.value, bo.value, o.value, n.value, ld.value, _layer_cols(n.value, sp.value)))
         return numel.value, out
 
     @staticmethod
@@ -124,10 +134,10 @@ class Agent(ABC):
     def _write_net(self, net_id, module, names, group=0):
         numel, layers = self._layout(net_id)
         blob = np.zeros(numel, np.float32)
-        for (wo, bo, o, n, ld), lin in zip(layers, self._linears(module, names)):
+        for (wo, bo, o, n, ld, cols), lin in zip(layers, self._linears(module, names)):
             w = lin.weight.detach().cpu().numpy()
             assert w.shape == (o, n), f"network shape mismatch: {w.shape} vs {(o, n)}"
-            blob[wo:wo + o * ld].reshape(o, ld)[:, :n] = w
+            blob[wo:wo + o * ld].reshape(o, ld)[:, cols] = w
             blob[bo:bo + o] = lin.bias.detach().cpu().numpy()
         _lib.check(self._lib.b200rl_agent_write(self._h, net_id, 0, group, blob.ctypes.data, _stream()))
 
@@ -146,8 +156,8 @@ class Agent(ABC):
     def _read_net_into(self, net_id, module, names, group=0):
         blob, layers = self._read_blob(net_id, 0, group)
         with torch.no_grad():
-            for (wo, bo, o, n, ld), lin in zip(layers, self._linears(module, names)):
-                lin.weight.copy_(torch.from_numpy(blob[wo:wo + o * ld].reshape(o, ld)[:, :n].copy()))
+            for (wo, bo, o, n, ld, cols), lin in zip(layers, self._linears(module, names)):
+                lin.weight.copy_(torch.from_numpy(blob[wo:wo + o * ld].reshape(o, ld)[:, cols].copy()))
                 lin.bias.copy_(torch.from_numpy(blob[bo:bo + o].copy()))
 
     def _push(self):
@@ -408,12 +418,15 @@ class Agent(ABC):
         ss, ac, rw, nd, gs = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
         _lib.check(self._lib.b200rl_agent_io(self._h, C.byref(ss), C.byref(ac), C.byref(rw), C.byref(nd), C.byref(gs)))
         B, S, A, G = self.batch_size, self.state_dim, self.action_dim, self.n_seeds
+        lds, lda = C.c_int(), C.c_int()
+        _lib.check(self._lib.b200rl_agent_io_ld(self._h, C.byref(lds), C.byref(lda)))
+        lds, lda = lds.value, lda.value  # rows of the state / action buffers start every round_up(width, 4) floats
         if G == 1:
-            view = lambda ptr, d: torch.as_tensor(_DeviceView(ptr, (B, d), self), device=self.device)  # noqa: E731
+            view = lambda ptr, d, ld: torch.as_tensor(_DeviceView(ptr, (B, d), self, strides=(4 * ld, 4)), device=self.device)  # noqa: E731
         else:  # [n_seeds, B, d] views strided by the engine's per-seed arena
-            view = lambda ptr, d: torch.as_tensor(_DeviceView(ptr, (G, B, d), self, strides=(4 * gs.value, 4 * d, 4)), device=self.device)  # noqa: E731
-        return {"state": view(ss.value, S), "action": view(ac.value, A), "reward": view(rw.value, 1),
-                "next_state": view(ss.value + 4 * B * S, S), "done": view(nd.value, 1)}
+            view = lambda ptr, d, ld: torch.as_tensor(_DeviceView(ptr, (G, B, d), self, strides=(4 * gs.value, 4 * ld, 4)), device=self.device)  # noqa: E731
+        return {"state": view(ss.value, S, lds), "action": view(ac.value, A, lda), "reward": view(rw.value, 1, 1),
+                "next_state": view(ss.value + 4 * B * lds, S, lds), "done": view(nd.value, 1, 1)}
 
     def _adopt_sink(self, replay_buffer):
         if replay_buffer is None or not getattr(replay_buffer, "zero_copy", False):

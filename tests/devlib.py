@@ -132,7 +132,12 @@ class Dev:
         for i in range(nl.value):
             wo, bo, o, n, ld = C.c_int64(), C.c_int64(), C.c_int(), C.c_int(), C.c_int()
             self.check(self.lib.b200rl_agent_layer_info(h, net, i, C.byref(wo), C.byref(bo), C.byref(o), C.byref(n), C.byref(ld)))
-            layers.append((wo.value, bo.value, o.value, n.value, ld.value))
+            sp = C.c_int()
+            self.check(self.lib.b200rl_agent_layer_split(h, net, i, C.byref(sp)))
+            # physical columns of the n logical input columns (a critic's first layer pads its state block to 4 floats)
+            s4 = (sp.value + 3) // 4 * 4
+            cols = slice(0, n.value) if not sp.value else np.r_[0:sp.value, s4:s4 + n.value - sp.value]
+            layers.append((wo.value, bo.value, o.value, n.value, ld.value, cols))
         return numel.value, layers
 
     def pack_net(self, h, net, tensors):
@@ -140,17 +145,17 @@ class Dev:
         numel, layers = self.net_layout(h, net)
         blob = np.zeros(numel, np.float32)
         assert len(layers) == len(tensors)
-        for (wo, bo, o, n, ld), (w, b) in zip(layers, tensors):
+        for (wo, bo, o, n, ld, cols), (w, b) in zip(layers, tensors):
             assert w.shape == (o, n), (w.shape, o, n)
-            blob[wo:wo + o * ld].reshape(o, ld)[:, :n] = w
+            blob[wo:wo + o * ld].reshape(o, ld)[:, cols] = w
             blob[bo:bo + o] = b
         return blob
 
     def unpack_net(self, h, net, blob):
         numel, layers = self.net_layout(h, net)
         out = []
-        for (wo, bo, o, n, ld) in layers:
-            out.append((blob[wo:wo + o * ld].reshape(o, ld)[:, :n].copy(), blob[bo:bo + o].copy()))
+        for (wo, bo, o, n, ld, cols) in layers:
+            out.append((blob[wo:wo + o * ld].reshape(o, ld)[:, cols].copy(), blob[bo:bo + o].copy()))
         return out
 
     def write_net(self, h, net, tensors, which=0, group=0):

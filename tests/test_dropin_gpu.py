@@ -172,7 +172,9 @@ def test_zero_copy_sample_hand_off():
     for x, y in zip(o1, o0):
         assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]) and x[2] == y[2] and x[3] == y[3]
     assert batches1[1] is a1._inbox and batches1[2] is batches1[1]          # aliasing, from the second call on
-    assert batches1[1]["next_state"].data_ptr() == batches1[1]["state"].data_ptr() + 4 * 256 * a1.state_dim
+    # (rows of the engine's state buffer start every round_up(state_dim, 4) floats: 16-byte aligned operands)
+    assert batches1[1]["state"].stride(0) == (a1.state_dim + 3) // 4 * 4
+    assert batches1[1]["next_state"].data_ptr() == batches1[1]["state"].data_ptr() + 4 * 256 * batches1[1]["state"].stride(0)
     assert batches0[1] is not batches0[2] and a0._inbox is None or batches0[1] is not a0._inbox
     # another agent fed from the same buffer takes the staged path and then becomes the sink
     other = TD7("Hopper-v4", use_lap=True)
