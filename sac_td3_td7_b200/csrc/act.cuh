@@ -11,9 +11,10 @@
 // through distributed shared memory, and one cluster barrier separates the layers.  The observation may live in
 // pinned host memory (read over the bus by the kernel itself) and the action may be written to a pinned host mailbox
 // followed by a sequence tag, so a host-to-host call is: memcpy into the slot, one launch, poll the tag.
-// Weights do not depend on the observation: every CTA requests its slice of ALL later layers (cp.async into ~165 KB of
-// shared memory) before the first phase, so the six dependent phases pay one L2 round trip between them instead of one
-// each (TD7: 14.4 -> see profiles/README.md); only the first phase, which needs its weights at once, reads them directly.
+// Option (B200RL_ACT_PREFETCH=1, measured and left off): weights do not depend on the observation, so every CTA can
+// request its slice of ALL later layers (cp.async into ~165 KB of shared memory) before the first phase.  It changes
+// nothing -- TD7 15.4 us per back-to-back launch against 14.4 us, TD3 8.2 against 6.2 -- the ~2.7 us a phase costs is
+// the warp reductions, the DSMEM push and the cluster barrier, not the weight reads (which come from L2 anyway).
 #pragma once
 #include "gemm.cuh"
 #include "ops.cuh"

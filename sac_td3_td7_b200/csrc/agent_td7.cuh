@@ -45,6 +45,8 @@ struct TD7Agent : AgentBase {
   // launch tables
   GemmTable E[16], C[24], Aa[24];
   GemmTable We[6];         // encoder weight gradients (+Adam), one launch per layer
+  GemmTable Cq[3];         // one agent: the current critics' forward q1 q2 q3 as a branch of its own (split_q)
+  bool split_q = false;
   GemmTable C2v[2];        // second launch of the critic chain, without / with the actor step's l0(s)
   GemmTable Wq[4], Wp[4];  // critic / policy weight gradients (+Adam), one launch per layer: [0] = last layer
   RowTable En[2], Cn[4], An[4];
@@ -184,12 +186,27 @@ struct TD7Agent : AgentBase {
       pn.aux = noise.p; pn.aux_ld = noise.ld; pn.aux_gs = noise.gs; pn.noise_sigma = sigma; pn.noise_clip = clipv;
       B200_TRY(up(C[6], kFwd, PV{pn, fwd_problem(fe, 5, {fa2}, zsa_f, kActNone)}));
     }
-    B200_TRY(up(C[7], kFwd, PV{fwd_problem(fet, 3, {zs_t, a_next}, ta1, kActElu), fwd_problem(qt[0], 0, {s_nxt, a_next}, tq0[0], kActNone),
-                               fwd_problem(qt[1], 0, {s_nxt, a_next}, tq0[1], kActNone), fwd_problem(q[0], 1, {cq0n[0], zsa_f, zs_f}, cqa[0], kActElu),
-                               fwd_problem(q[1], 1, {cq0n[1], zsa_f, zs_f}, cqa[1], kActElu)}));
+    // The current critics' forward (three launches) has slack -- the target side still has six launches to go when its
+    // inputs are ready -- so for one agent it runs as its own branch: riding with the target chain's launches it made
+    // the first of them 320 tiles (a second wave at two CTAs per SM for 24 CTAs: 16 us instead of ~7).  Stacked seeds
+    // fill the machine either way and keep the grouped launches.
+    split_q = (G == 1);
+    if (split_q) {
+      B200_TRY(up(C[7], kFwd, PV{fwd_problem(fet, 3, {zs_t, a_next}, ta1, kActElu), fwd_problem(qt[0], 0, {s_nxt, a_next}, tq0[0], kActNone),
+                                 fwd_problem(qt[1], 0, {s_nxt, a_next}, tq0[1], kActNone)}));
+      B200_TRY(up(C[8], kFwd, PV{fwd_problem(fet, 4, {ta1}, ta2, kActElu)}));
+      B200_TRY(up(C[9], kFwd, PV{fwd_problem(fet, 5, {ta2}, zsa_t, kActNone)}));
+      B200_TRY(up(Cq[0], kFwd, PV{fwd_problem(q[0], 1, {cq0n[0], zsa_f, zs_f}, cqa[0], kActElu), fwd_problem(q[1], 1, {cq0n[1], zsa_f, zs_f}, cqa[1], kActElu)}, true));
+      B200_TRY(up(Cq[1], kFwd, PV{fwd_problem(q[0], 2, {cqa[0]}, cqb[0], kActElu), fwd_problem(q[1], 2, {cqa[1]}, cqb[1], kActElu)}, true));
+      B200_TRY(up(Cq[2], kFwd, PV{fwd_problem(q[0], 3, {cqb[0]}, qv[0], kActNone), fwd_problem(q[1], 3, {cqb[1]}, qv[1], kActNone)}, true));
+    } else {
+      B200_TRY(up(C[7], kFwd, PV{fwd_problem(fet, 3, {zs_t, a_next}, ta1, kActElu), fwd_problem(qt[0], 0, {s_nxt, a_next}, tq0[0], kActNone),
+                                 fwd_problem(qt[1], 0, {s_nxt, a_next}, tq0[1], kActNone), fwd_problem(q[0], 1, {cq0n[0], zsa_f, zs_f}, cqa[0], kActElu),
+                                 fwd_problem(q[1], 1, {cq0n[1], zsa_f, zs_f}, cqa[1], kActElu)}));
+      B200_TRY(up(C[8], kFwd, PV{fwd_problem(fet, 4, {ta1}, ta2, kActElu), fwd_problem(q[0], 2, {cqa[0]}, cqb[0], kActElu), fwd_problem(q[1], 2, {cqa[1]}, cqb[1], kActElu)}));
+      B200_TRY(up(C[9], kFwd, PV{fwd_problem(fet, 5, {ta2}, zsa_t, kActNone), fwd_problem(q[0], 3, {cqb[0]}, qv[0], kActNone), fwd_problem(q[1], 3, {cqb[1]}, qv[1], kActNone)}));
+    }
     B200_TRY(upn(Cn[3], false, {nf(tq0[0], tq0n[0]), nf(tq0[1], tq0n[1])}));
-    B200_TRY(up(C[8], kFwd, PV{fwd_problem(fet, 4, {ta1}, ta2, kActElu), fwd_problem(q[0], 2, {cqa[0]}, cqb[0], kActElu), fwd_problem(q[1], 2, {cqa[1]}, cqb[1], kActElu)}));
-    B200_TRY(up(C[9], kFwd, PV{fwd_problem(fet, 5, {ta2}, zsa_t, kActNone), fwd_problem(q[0], 3, {cqb[0]}, qv[0], kActNone), fwd_problem(q[1], 3, {cqb[1]}, qv[1], kActNone)}));
     B200_TRY(up(C[10], kFwd, PV{fwd_problem(qt[0], 1, {tq0n[0], zsa_t, zs_t}, tqa[0], kActElu), fwd_problem(qt[1], 1, {tq0n[1], zsa_t, zs_t}, tqa[1], kActElu)}));
     B200_TRY(up(C[11], kFwd, PV{fwd_problem(qt[0], 2, {tqa[0]}, tqb[0], kActElu), fwd_problem(qt[1], 2, {tqa[1]}, tqb[1], kActElu)}));
     B200_TRY(up(C[12], kFwd, PV{fwd_problem(qt[0], 3, {tqb[0]}, qtv[0], kActNone), fwd_problem(qt[1], 3, {tqb[1]}, qtv[1], kActNone)}));
@@ -278,6 +295,7 @@ struct TD7Agent : AgentBase {
       a->add_row_ops(Cn[2].h_ops, false);
       if (actor) for (int i = 0; i <= 5; ++i) a->add_gemm_table(Aa[i]);
       for (int i : {4, 5, 6, 7}) a->add_gemm_table(C[i]);
+      if (split_q) for (int i = 0; i < 3; ++i) a->add_gemm_table(Cq[i]);
       a->add_row_ops(Cn[3].h_ops, false);
       for (int i : {8, 9, 10, 11, 12}) a->add_gemm_table(C[i]);
       B200_TRY(a->build(&arena, G, sm_count()));
@@ -410,12 +428,18 @@ struct TD7Agent : AgentBase {
     }
     GL(C[4], M); GL(C[5], M);
     B200_TRY(fork.link(sP, M));  // smoothing noise for the policy's last layer; counters for the loss / Adam
-    GL(C[6], M); GL(C[7], M);
+    GL(C[6], M);
+    if (split_q) {  // (sP is idle between the noise and the LAP write-back)
+      B200_TRY(fork.link(M, sP));
+      GL(Cq[0], sP); GL(Cq[1], sP); GL(Cq[2], sP);
+    }
+    GL(C[7], M);
     B200_TRY(fork.link(M, sN));
     RL(Cn[3], sN);
     GL(C[8], M); GL(C[9], M);
     B200_TRY(fork.link(sN, M));
     GL(C[10], M); GL(C[11], M); GL(C[12], M);
+    if (split_q) B200_TRY(fork.link(sP, M));
     B200_TRY(launch_critic_loss(M));
     const bool fix_tree = use_lap && bound != nullptr;  // LAP write-back + sum-tree repair, off the chain
     if (fix_tree) {

@@ -324,7 +324,10 @@ static int build_act_path(b200rl_agent* h) {
       aa.pre_off[l] = (int)tot;
       tot += (long long)ceil_div(aa.L[l].out, kActCluster) * aa.L[l].ld;
     }
-    static const bool pre = [] { const char* e = getenv("B200RL_ACT_PREFETCH"); return e ? atoi(e) != 0 : true; }();
+    // OFF by default: measured on B200 it does not pay -- back-to-back launches 15.4 us with it, 14.4 us without (TD7), 8.2
+    // against 6.2 us (TD3): a phase costs ~2.7 us whether its weights wait in shared memory or come from L2, so the
+    // chain is bound by the reduction / DSMEM push / cluster-barrier sequence, not by the weight reads.
+    static const bool pre = [] { const char* e = getenv("B200RL_ACT_PREFETCH"); return e ? atoi(e) != 0 : false; }();
     // (only while every cluster of the launch is resident at once: with hundreds of stacked seeds the kernel runs in
     // waves, where many small CTAs per SM hide the weight reads better than one CTA holding 165 KB)
     if (!pre || a.G * kActCluster > 148 || (round_up(S, 4) + 4ll * aa.vmax + tot) * (long long)sizeof(float) > 200 * 1024) {
