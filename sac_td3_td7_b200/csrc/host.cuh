@@ -233,7 +233,7 @@ inline int gemm_table_upload(GemmTable* t, int mode, std::vector<GemmProblem>& p
 #ifndef B200_EMU
     if (want_tc && tc_eligible(p)) { tc.push_back(p); continue; }
 #endif
-    if (want_narrow && mode == kWgrad && narrow_wgrad_eligible(p)) { nw.push_back(p); continue; }
+    if (want_narrow && mode == kWgrad && (narrow_wgrad_eligible(p) || narrow_wgrad_t_eligible(p))) { nw.push_back(p); continue; }
     if (want_narrow && narrow_rows_eligible(p, mode)) { nr.push_back(p); continue; }
     if ((want_tc || want_narrow) && mode == kWgrad && p.nseg == 1 && p.seg[0].b_ones && p.J == 1) { bias.push_back(p); continue; }
     ff.push_back(p);
@@ -248,14 +248,21 @@ inline int gemm_table_upload(GemmTable* t, int mode, std::vector<GemmProblem>& p
     for (size_t i = 0; i < nw.size(); ++i) {
       const GemmProblem& p = nw[i];
       NarrowWgrad& q = t->launch_nw.p[i];
-      q.dZ = p.seg[0].A; q.dz_gs = p.seg[0].a_gs; q.dz_ld = p.seg[0].a_ld; q.rows = p.seg[0].len; q.out = p.I;
-      q.X = p.seg[0].B; q.x_gs = p.seg[0].b_gs; q.x_ld = p.seg[0].b_ld; q.J = p.J;
+      q.transposed = narrow_wgrad_eligible(p) ? 0 : 1;
+      q.rows = p.seg[0].len;
+      if (!q.transposed) {
+        q.dZ = p.seg[0].A; q.dz_gs = p.seg[0].a_gs; q.dz_ld = p.seg[0].a_ld; q.out = p.I;
+        q.X = p.seg[0].B; q.x_gs = p.seg[0].b_gs; q.x_ld = p.seg[0].b_ld; q.J = p.J;
+      } else {  // stream the wide operand (the layer's input X), broadcast the few columns of dZ
+        q.dZ = p.seg[0].B; q.dz_gs = p.seg[0].b_gs; q.dz_ld = p.seg[0].b_ld; q.out = p.J;
+        q.X = p.seg[0].A; q.x_gs = p.seg[0].a_gs; q.x_ld = p.seg[0].a_ld; q.J = p.I;
+      }
       q.C = p.C; q.P = p.P; q.M = p.M; q.V = p.V;
       q.p_gs = p.P ? p.p_gs : p.c_gs; q.p_ld = p.P ? p.p_ld : p.c_ld;
       q.adam = p.adam;
-      q.jchunks = ceil_div(p.J, kNwCols);
+      q.jchunks = ceil_div(q.J, kNwCols);
       q.unit_begin = units;
-      units += q.jchunks * ceil_div(p.I, kNwThreads);
+      units += q.jchunks * ceil_div(q.out, kNwThreads);
     }
     t->launch_nw.nprob = (int)nw.size();
     t->launch_nw.total_units = units;
@@ -266,7 +273,7 @@ inline int gemm_table_upload(GemmTable* t, int mode, std::vector<GemmProblem>& p
       bool folded = false;
       for (size_t i = 0; i < nw.size() && !folded; ++i) {
         NarrowWgrad& q = t->launch_nw.p[i];
-        if (q.dZ == b.seg[0].A && q.dz_gs == b.seg[0].a_gs && q.out == b.I && !q.bP && !q.bC && (b.P ? b.p_gs : b.c_gs) == q.p_gs && (!b.P || b.adam == q.adam || !q.P)) {
+        if (!q.transposed && q.dZ == b.seg[0].A && q.dz_gs == b.seg[0].a_gs && q.out == b.I && !q.bP && !q.bC && (b.P ? b.p_gs : b.c_gs) == q.p_gs && (!b.P || b.adam == q.adam || !q.P)) {
           q.bC = b.C; q.bP = b.P; q.bM = b.M; q.bV = b.V;
           if (!q.adam) q.adam = b.adam;
           folded = true;

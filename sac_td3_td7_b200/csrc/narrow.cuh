@@ -31,6 +31,7 @@ struct NarrowWgrad {
   float* C; float* P; float* M; float* V;                  // gradient out (may be null) / Adam state, [out][p_ld]
   long long p_gs; int p_ld;
   int unit_begin, jchunks;
+  int transposed, pad;  // 1: the result block is stored transposed, W[j][i] (a layer with a few OUTPUTS: the roles of dZ and X swap)
   // bias of the same layer (column sums of dZ), folded into the pass over dZ of column chunk 0 (null: none)
   float* bC; float* bP; float* bM; float* bV;
   const AdamScalars* adam;
@@ -97,6 +98,8 @@ __global__ void __launch_bounds__(kNwThreads, 2) narrow_wgrad_kernel(const __gri
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = make_float2(0.f, 0.f);
   float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+  AdamScalars ad = {};  // (requested now: its round trip hides behind the stream instead of opening the epilogue)
+  if (q.P || (with_bias && q.bP)) ad = *q.adam;
   for (int b0 = 0; b0 < q.rows; b0 += kNwRows) {
     const int nb = min(kNwRows, q.rows - b0);
     const int nst = (nb + kNwStageRows - 1) / kNwStageRows;
@@ -121,18 +124,28 @@ __global__ void __launch_bounds__(kNwThreads, 2) narrow_wgrad_kernel(const __gri
       if (st < nst) issue(st);
       cp_async_commit();
     }
-    // X: eight independent read-only loads in flight per thread
-    if (!(L.dbg & 1))
-    for (int it = 0; it < kNwRows * kNwCols / kNwThreads; it += 8) {
-      float xv[8];
+    // X: only the jn live columns are read (read-only path, sixteen independent loads in flight per thread); the rest of
+    // a 32-wide row is zero
+    if (!(L.dbg & 1)) {
+      if (jn < kNwCols)
+        for (int idx = threadIdx.x; idx < kNwRows * kNwCols; idx += kNwThreads)
+          if ((idx & (kNwCols - 1)) >= jn || idx / kNwCols >= nb) Xs[idx] = 0.f;
+      const int live = nb * jn;
+      for (int e0 = threadIdx.x; e0 < live; e0 += 16 * kNwThreads) {
+        float xv[16];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int idx = (it + k) * kNwThreads + threadIdx.x;
-        const int b = idx / kNwCols, j = idx - b * kNwCols;
-        xv[k] = (b < nb && j < jn) ? __ldg(x + (long long)(b0 + b) * q.x_ld + j) : 0.f;
+        for (int k = 0; k < 16; ++k) {
+          const int e = e0 + k * kNwThreads;
+          const int b = e / jn, j = e - b * jn;
+          xv[k] = e < live ? __ldg(x + (long long)(b0 + b) * q.x_ld + j) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int e = e0 + k * kNwThreads;
+          const int b = e / jn, j = e - b * jn;
+          if (e < live) Xs[b * kNwCols + j] = xv[k];
+        }
       }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) Xs[(it + k) * kNwThreads + threadIdx.x] = xv[k];
     }
     for (int st = 0; st < nst; ++st) {
       cp_async_wait<kNwStages - 2>();
@@ -161,10 +174,9 @@ __global__ void __launch_bounds__(kNwThreads, 2) narrow_wgrad_kernel(const __gri
       }
   }
   __syncthreads();
-  AdamScalars ad = {};
-  if (q.P || (with_bias && q.bP)) ad = *q.adam;
   const int rows_here = min(kNwThreads, q.out - i0);
-  const long long base = (long long)g * q.p_gs + (long long)i0 * q.p_ld + j0;
+  const bool tr = q.transposed != 0;
+  const long long base = (long long)g * q.p_gs + (tr ? (long long)j0 * q.p_ld + i0 : (long long)i0 * q.p_ld + j0);
   const int total = rows_here * jn;
   // element e -> (row e / jn, column e % jn): runs of jn consecutive floats of W's rows; eight elements in flight
   for (int e0 = threadIdx.x; e0 < total; e0 += 8 * kNwThreads) {
@@ -175,8 +187,10 @@ __global__ void __launch_bounds__(kNwThreads, 2) narrow_wgrad_kernel(const __gri
     for (int k = 0; k < 8; ++k) {
       const int e = e0 + k * kNwThreads;
       ok[k] = e < total;
-      const int r = ok[k] ? e / jn : 0, c = ok[k] ? e - r * jn : 0;
-      off[k] = base + (long long)r * q.p_ld + c;
+      int r, c;  // (consecutive e run along the contiguous direction of W)
+      if (tr) { c = ok[k] ? e / rows_here : 0; r = ok[k] ? e - c * rows_here : 0; }
+      else { r = ok[k] ? e / jn : 0; c = ok[k] ? e - r * jn : 0; }
+      off[k] = base + (tr ? (long long)c * q.p_ld + r : (long long)r * q.p_ld + c);
       gq[k] = G[r * kGs + c];
       if (ok[k] && q.P) { pp[k] = q.P[off[k]]; mm[k] = q.M[off[k]]; vv[k] = q.V[off[k]]; }
     }
@@ -192,17 +206,18 @@ __global__ void __launch_bounds__(kNwThreads, 2) narrow_wgrad_kernel(const __gri
   }
   if (with_bias && tj == 0) {
     const float bs[4] = {bsum.x, bsum.y, bsum.z, bsum.w};
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int r = i0 + 4 * ti + a;
-      if (r >= q.out) break;
-      const long long o = (long long)g * q.p_gs + r;
+    const long long o = (long long)g * q.p_gs + i0 + 4 * ti;
+    const int nv = min(4, q.out - (i0 + 4 * ti));
+    if (nv > 0) {
+      float p[4], m[4], v[4];
       if (q.bP) {
-        float p = q.bP[o], m = q.bM[o], v = q.bV[o];
-        adam_update(bs[a], p, m, v, ad);
-        q.bP[o] = p; q.bM[o] = m; q.bV[o] = v;
+        load_quad(p, q.bP + o, nv); load_quad(m, q.bM + o, nv); load_quad(v, q.bV + o, nv);
+        float gq[4] = {bs[0], bs[1], bs[2], bs[3]};
+#pragma unroll
+        for (int a = 0; a < 4; ++a) adam_update(gq[a], p[a], m[a], v[a], ad);
+        store_quad(q.bP + o, p, nv); store_quad(q.bM + o, m, nv); store_quad(q.bV + o, v, nv);
       }
-      if (q.bC) q.bC[o] = bs[a];
+      if (q.bC) store_quad(q.bC + o, bs, nv);
     }
   }
 }
@@ -366,6 +381,10 @@ __global__ void __launch_bounds__(256) rank1_dgrad_kernel(const __grid_constant_
 inline bool ptr16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 inline bool narrow_wgrad_eligible(const GemmProblem& p) {
   return p.nseg == 1 && !p.seg[0].b_ones && p.J < 64 && (p.P != nullptr || p.C != nullptr);
+}
+// dW[i, :] for a layer with at most 32 outputs (action head, scalar head): computed as its transpose
+inline bool narrow_wgrad_t_eligible(const GemmProblem& p) {
+  return p.nseg == 1 && !p.seg[0].b_ones && p.I <= kNwCols && p.J >= 64 && (p.P != nullptr || p.C != nullptr);
 }
 inline bool narrow_rows_eligible(const GemmProblem& p, int mode) {
   if (mode == kWgrad || p.J > kNrMaxJ) return false;
