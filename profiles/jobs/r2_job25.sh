@@ -1,0 +1,4 @@
+cd /root/repo
+w=td7_humanoid_pop256
+timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${w}_r02.csv python profiles/prof_update.py $w 4 > gpurun_out/r2_ncu_$w.log 2>&1
+python profiles/summarize_launches.py gpurun_out/launches_${w}_r02.csv | head -20

@@ -232,6 +232,28 @@ inline int gemm_table_upload(GemmTable* t, int mode, std::vector<GemmProblem>& p
     if (want_narrow && rank1_eligible(p, mode)) { r1.push_back(p); continue; }
 #ifndef B200_EMU
     if (want_tc && tc_eligible(p)) { tc.push_back(p); continue; }
+    // A weight gradient whose input width is not a tensor-core tile width (Humanoid's 376 observation columns) is cut along
+    // its columns into tcgen05 problems of <= 256 columns, multiples of 32 (TMA-addressable), and a narrow remainder:
+    // 376 = 256 + 96 + 24.  As 32 x 32 FFMA tiles these gradients were 20 % of a 256-seed Humanoid update.
+    if (want_tc && want_narrow && mode == kWgrad && p.nseg == 1 && !p.seg[0].b_ones && p.J > kTcNMax / 4 && (p.I % kTcM) == 0 && (p.seg[0].b_ld & 3) == 0 &&
+        (p.P || p.C) && (!p.P || (p.p_ld & 3) == 0)) {
+      int j0 = 0;
+      auto sub = [&](int jn) {
+        GemmProblem q = p;
+        q.J = jn;
+        q.seg[0].B = p.seg[0].B + j0;
+        if (q.C) q.C += j0;
+        if (q.P) { q.P += j0; q.M += j0; q.V += j0; }
+        return q;
+      };
+      while (p.J - j0 >= 64) {
+        const int jn = std::min(kTcNMax, (p.J - j0) / 32 * 32);
+        tc.push_back(sub(jn));
+        j0 += jn;
+      }
+      if (p.J - j0 > 0) nw.push_back(sub(p.J - j0));
+      continue;
+    }
 #endif
     if (want_narrow && mode == kWgrad && (narrow_wgrad_eligible(p) || narrow_wgrad_t_eligible(p))) { nw.push_back(p); continue; }
     if (want_narrow && narrow_rows_eligible(p, mode)) { nr.push_back(p); continue; }
