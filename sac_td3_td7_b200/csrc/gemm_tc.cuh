@@ -224,6 +224,8 @@ __device__ __forceinline__ void tc_epilogue_warp(const GemmProblem& sp, int g, i
   for (int cc = 0; cc < ncb; ++cc) {
     const int col0 = colhalf + cc * 32;
     if (col0 >= n_pad) break;  // uniform across the warp
+    // (requested before the TMEM load and the transposition, consumed after them)
+    const float bias = (MODE == kFwd && sp.bias && col0 + lane < J) ? sp.bias[(long long)g * sp.bias_gs + col0 + lane] : 0.f;
     {
       float v[32];
       if (total_chunks > 0) {
@@ -242,12 +244,33 @@ __device__ __forceinline__ void tc_epilogue_warp(const GemmProblem& sp, int g, i
     constexpr int U = 8;  // rows in flight: all global loads of a batch are issued before the first use
     if (MODE == kFwd) {
       // (the smoothing-noise epilogue never reaches this kernel: its layer has J = action_dim < 64)
-      const float bias = (sp.bias && col_ok) ? sp.bias[(long long)g * sp.bias_gs + col] : 0.f;
       float* cptr = sp.C + (long long)g * sp.c_gs + (long long)row_base * sp.c_ld + col;
       if (col_ok) {
-        for (int rr = 0; rr < nrows; ++rr) {
-          *cptr = act_forward(st[rr * 33 + lane] + bias, sp.act);
-          cptr += sp.c_ld;
+        // The activation is resolved once per block and the 32 rows go in unrolled batches of eight independent
+        // load -> activation -> store chains: as one rolled loop with the activation switch inside, a 128 x 256 tile's
+        // epilogue was a ~12 us dependent chain per warp (what a K = 27 first-layer tile took in total), longer than
+        // the loads of a K = 256 tile.  ELU uses ex2.approx: |error| <= 2 ulp of exp(x), far inside the TF32 tolerance
+        // of this path (the fp32 single-agent kernels keep expm1f).
+        const long long ld = sp.c_ld;
+        auto rows = [&](auto f) {
+          if (nrows == 32) {
+#pragma unroll
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+              float y[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) y[u] = f(st[(r0 + u) * 33 + lane] + bias);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) cptr[(long long)(r0 + u) * ld] = y[u];
+            }
+          } else {
+            for (int rr = 0; rr < nrows; ++rr) cptr[(long long)rr * ld] = f(st[rr * 33 + lane] + bias);
+          }
+        };
+        switch (sp.act) {
+          case kActRelu: rows([](float v) { return v > 0.f ? v : 0.f; }); break;
+          case kActElu: rows([](float v) { return v > 0.f ? v : __expf(v) - 1.f; }); break;
+          case kActTanh: rows([](float v) { return tanhf(v); }); break;
+          default: rows([](float v) { return v; }); break;
         }
       }
     } else if (MODE == kDgrad) {

@@ -9,7 +9,7 @@
 // Here each one is a single pass over its one large operand:
 //   narrow_wgrad_kernel  dW[:, j0:j0+32] = dZ^T X[:, j0:j0+32] (+ the bias gradient, + Adam in place): thread = output
 //                        row, the <= 32 input columns broadcast from shared memory, dZ read once, coalesced;
-//   narrow_rows_kernel   Y[i, 0:J] = epilogue(sum_seg X_seg[i, :] . B_seg), J <= 8 (forward and dgrad layouts): eight
+//   narrow_rows_kernel   Y[i, 0:J] = epilogue(sum_seg X_seg[i, :] . B_seg), J <= 32 (forward and dgrad layouts): eight
 //                        lanes per row with 128-bit loads, the small operand staged in shared memory;
 //   rank1_dgrad_kernel   dX[i, j] = dz[i] * w[j] (* act'(H[i, j])): elementwise.
 // All three are plain CUDA C (they also run under the host emulation of tests/cuemu).
@@ -223,7 +223,8 @@ __global__ void __launch_bounds__(kNwThreads, 2) narrow_wgrad_kernel(const __gri
 }
 
 // ----------------------------------------------------------------------------- narrow outputs (forward / dgrad, J <= 8)
-constexpr int kNrMaxJ = 8;
+constexpr int kNrMaxJ = 8;      // output columns per pass
+constexpr int kNrMaxCols = 32;  // widest output handled (in passes of kNrMaxJ)
 constexpr int kNrMaxK = 1024;   // total reduction length over the segments
 constexpr int kNrThreads = 256; // 32 rows x 8 lanes
 struct NarrowRows {
@@ -249,92 +250,98 @@ __global__ void __launch_bounds__(kNrThreads) narrow_rows_kernel(const __grid_co
   while (pi + 1 < L.nprob && (int)blockIdx.x >= L.p[pi + 1].unit_begin) ++pi;
   const NarrowRows& q = L.p[pi];
   const int g = blockIdx.y;
-  const int J = q.J;
-  // stage the small operand: Ws[j][k] over the concatenated reduction index k
-  int koff = 0;
-  for (int s = 0; s < q.nseg; ++s) {
-    const GemmSeg& sg = q.seg[s];
-    const float* Bp = sg.B + (long long)g * sg.b_gs;
-    // (read-only loads, four in flight per thread: see narrow_wgrad_kernel)
-    for (int base = 0; base < sg.len * J; base += 4 * kNrThreads) {
-      float wv[4];
-      int wj[4], wr[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int idx = base + k * kNrThreads + (int)threadIdx.x;
-        const bool ok = idx < sg.len * J;
-        int r, j;
-        if (MODE == kFwd) { j = idx / sg.len; r = idx - j * sg.len; }
-        else { r = idx / J; j = idx - r * J; }
-        wj[k] = ok ? j : -1; wr[k] = r;
-        wv[k] = ok ? __ldg(Bp + (MODE == kFwd ? (long long)j * sg.b_ld + r : (long long)r * sg.b_ld + j)) : 0.f;
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (wj[k] >= 0) Ws[wj[k]][koff + wr[k]] = wv[k];
-    }
-    koff += sg.len;
-  }
-  __syncthreads();
   const int row = ((int)blockIdx.x - q.unit_begin) * 32 + (threadIdx.x >> 3), lq = threadIdx.x & 7;
   const bool valid = row < q.I;
-  float acc[kNrMaxJ];
+  // output columns in passes of eight (Humanoid's 17-wide action head: three passes over rows that stay in L1 / L2)
+  for (int jb = 0; jb < q.J; jb += kNrMaxJ) {
+    const int J = min(kNrMaxJ, q.J - jb);
+    if (jb) __syncthreads();  // the previous pass has finished reading Ws
+    // stage the small operand: Ws[j][k] over the concatenated reduction index k
+    int koff = 0;
+    for (int s = 0; s < q.nseg; ++s) {
+      const GemmSeg& sg = q.seg[s];
+      const float* Bp = sg.B + (long long)g * sg.b_gs;
+      // (read-only loads, four in flight per thread: a plain load / store loop serialises on possible aliasing)
+      for (int base = 0; base < sg.len * J; base += 4 * kNrThreads) {
+        float wv[4];
+        int wj[4], wr[4];
 #pragma unroll
-  for (int j = 0; j < kNrMaxJ; ++j) acc[j] = 0.f;
-  koff = 0;
-  for (int s = 0; s < q.nseg; ++s) {
-    const GemmSeg& sg = q.seg[s];
-    const float* a = sg.A + (long long)g * sg.a_gs + (long long)(valid ? row : 0) * sg.a_ld;
-    // (eligibility: len, a_ld multiples of 4 and 16-byte aligned bases) four 128-bit loads in flight per lane
-    for (int r0 = lq * 4; r0 < sg.len; r0 += 128) {
-      float4 xv[4];
+        for (int k = 0; k < 4; ++k) {
+          const int idx = base + k * kNrThreads + (int)threadIdx.x;
+          const bool ok = idx < sg.len * J;
+          int r, j;
+          if (MODE == kFwd) { j = idx / sg.len; r = idx - j * sg.len; }
+          else { r = idx / J; j = idx - r * J; }
+          wj[k] = ok ? j : -1; wr[k] = r;
+          wv[k] = ok ? __ldg(Bp + (MODE == kFwd ? (long long)(jb + j) * sg.b_ld + r : (long long)r * sg.b_ld + jb + j)) : 0.f;
+        }
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int r = r0 + 32 * t;
-        xv[t] = (valid && r < sg.len) ? *reinterpret_cast<const float4*>(a + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < 4; ++k)
+          if (wj[k] >= 0) Ws[wj[k]][koff + wr[k]] = wv[k];
       }
+      koff += sg.len;
+    }
+    __syncthreads();
+    float acc[kNrMaxJ];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int r = r0 + 32 * t;
-        if (r < sg.len) {
+    for (int j = 0; j < kNrMaxJ; ++j) acc[j] = 0.f;
+    koff = 0;
+    for (int s = 0; s < q.nseg; ++s) {
+      const GemmSeg& sg = q.seg[s];
+      const float* a = sg.A + (long long)g * sg.a_gs + (long long)(valid ? row : 0) * sg.a_ld;
+      // (eligibility: len, a_ld multiples of 4 and 16-byte aligned bases) four 128-bit loads in flight per lane
+      for (int r0 = lq * 4; r0 < sg.len; r0 += 128) {
+        float4 xv[4];
 #pragma unroll
-          for (int j = 0; j < kNrMaxJ; ++j) {
-            if (j < J) {
-              const float4 wv = *reinterpret_cast<const float4*>(&Ws[j][koff + r]);
-              acc[j] = fmaf(xv[t].x, wv.x, fmaf(xv[t].y, wv.y, fmaf(xv[t].z, wv.z, fmaf(xv[t].w, wv.w, acc[j]))));
+        for (int t = 0; t < 4; ++t) {
+          const int r = r0 + 32 * t;
+          xv[t] = (valid && r < sg.len) ? *reinterpret_cast<const float4*>(a + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int r = r0 + 32 * t;
+          if (r < sg.len) {
+#pragma unroll
+            for (int j = 0; j < kNrMaxJ; ++j) {
+              if (j < J) {
+                const float4 wv = *reinterpret_cast<const float4*>(&Ws[j][koff + r]);
+                acc[j] = fmaf(xv[t].x, wv.x, fmaf(xv[t].y, wv.y, fmaf(xv[t].z, wv.z, fmaf(xv[t].w, wv.w, acc[j]))));
+              }
             }
           }
         }
       }
+      koff += sg.len;
     }
-    koff += sg.len;
-  }
-  // the eight lanes of a row combine; lane j finishes output column j
-  float mine = 0.f;
+    // the eight lanes of a row combine; lane j finishes output column jb + j
+    float mine = 0.f;
 #pragma unroll
-  for (int j = 0; j < kNrMaxJ; ++j) {
-    float v = acc[j];
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    v += __shfl_xor_sync(0xffffffffu, v, 4);
-    if (j == lq) mine = v;
-  }
-  if (!valid || lq >= J) return;
-  float* c = q.C + (long long)g * q.c_gs + (long long)row * q.c_ld + lq;
-  float v = mine;
-  if (MODE == kFwd) {
-    if (q.bias) v += q.bias[(long long)g * q.bias_gs + lq];
-    if (q.act == kActTanhNoise) {
-      const float n = fminf(fmaxf(q.aux[(long long)g * q.aux_gs + (long long)row * q.aux_ld + lq] * q.noise_sigma, -q.noise_clip), q.noise_clip);
-      v = fminf(fmaxf(tanhf(v) + n, -1.f), 1.f);
-    } else {
-      v = act_forward(v, q.act);
+    for (int j = 0; j < kNrMaxJ; ++j) {
+      float v = acc[j];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      if (j == lq) mine = v;
     }
-  } else {
-    if (q.accumulate) v += *c;
-    if (q.aux) v *= act_backward(q.aux[(long long)g * q.aux_gs + (long long)row * q.aux_ld + lq], q.act);
+    if (valid && lq < J) {
+      const int col = jb + lq;
+      float* c = q.C + (long long)g * q.c_gs + (long long)row * q.c_ld + col;
+      float v = mine;
+      if (MODE == kFwd) {
+        if (q.bias) v += q.bias[(long long)g * q.bias_gs + col];
+        if (q.act == kActTanhNoise) {
+          const float n = fminf(fmaxf(q.aux[(long long)g * q.aux_gs + (long long)row * q.aux_ld + col] * q.noise_sigma, -q.noise_clip), q.noise_clip);
+          v = fminf(fmaxf(tanhf(v) + n, -1.f), 1.f);
+        } else {
+          v = act_forward(v, q.act);
+        }
+      } else {
+        if (q.accumulate) v += *c;
+        if (q.aux) v *= act_backward(q.aux[(long long)g * q.aux_gs + (long long)row * q.aux_ld + col], q.act);
+      }
+      *c = v;
+    }
   }
-  *c = v;
 }
 
 // ----------------------------------------------------------------------------- rank-1 dgrad (through a one-output layer)
@@ -387,7 +394,7 @@ inline bool narrow_wgrad_t_eligible(const GemmProblem& p) {
   return p.nseg == 1 && !p.seg[0].b_ones && p.I <= kNwCols && p.J >= 64 && (p.P != nullptr || p.C != nullptr);
 }
 inline bool narrow_rows_eligible(const GemmProblem& p, int mode) {
-  if (mode == kWgrad || p.J > kNrMaxJ) return false;
+  if (mode == kWgrad || p.J > kNrMaxCols) return false;
   int k = 0;
   for (int s = 0; s < p.nseg; ++s) {
     const GemmSeg& sg = p.seg[s];
