@@ -220,6 +220,8 @@ template <int MODE>
 __device__ __forceinline__ void tc_epilogue_warp(const GemmProblem& sp, int g, int I, int J, int n_pad, int i0, int rowgrp, int colhalf, float* st, int lane,
                                                  uint32_t tmem_acc, int total_chunks, int ncb = 4) {
   const int row_base = i0 + 32 * rowgrp;
+  AdamScalars sc = {};
+  if (MODE == kWgrad && sp.P) sc = *sp.adam;  // (once per tile, its round trip behind the accumulator wait of the first block)
 #pragma unroll 1
   for (int cc = 0; cc < ncb; ++cc) {
     const int col0 = colhalf + cc * 32;
@@ -277,52 +279,87 @@ __device__ __forceinline__ void tc_epilogue_warp(const GemmProblem& sp, int g, i
       float* cbase = sp.C + (long long)g * sp.c_gs + (long long)row_base * sp.c_ld + col;
       const float* hbase = sp.aux ? sp.aux + (long long)g * sp.aux_gs + (long long)row_base * sp.aux_ld + col : nullptr;
       const bool acc_in = sp.accumulate != 0;
-      for (int r0 = 0; r0 < nrows; r0 += U) {
-        float hv[U], cv[U];
+      // same shape as the forward epilogue: the derivative is resolved once per block, full blocks run in unrolled
+      // batches of eight rows with every global load of a batch issued before its first use
+      auto rows = [&](auto dact) {
+        if (nrows == 32 && col_ok) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const bool ok = col_ok && r0 + u < nrows;
-          hv[u] = (hbase && ok) ? hbase[(long long)(r0 + u) * sp.aux_ld] : 0.f;
-          cv[u] = (acc_in && ok) ? cbase[(long long)(r0 + u) * sp.c_ld] : 0.f;
-        }
+          for (int r0 = 0; r0 < 32; r0 += U) {
+            float hv[U], cv[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (col_ok && r0 + u < nrows) {
-            float x = st[(r0 + u) * 33 + lane] + cv[u];
-            if (hbase) x *= act_backward(hv[u], sp.act);
-            cbase[(long long)(r0 + u) * sp.c_ld] = x;
+            for (int u = 0; u < U; ++u) {
+              hv[u] = hbase ? hbase[(long long)(r0 + u) * sp.aux_ld] : 0.f;
+              cv[u] = acc_in ? cbase[(long long)(r0 + u) * sp.c_ld] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              float x = st[(r0 + u) * 33 + lane] + cv[u];
+              if (hbase) x *= dact(hv[u]);
+              cbase[(long long)(r0 + u) * sp.c_ld] = x;
+            }
+          }
+        } else {
+          for (int rr = 0; rr < nrows; ++rr) {
+            if (!col_ok) break;
+            float x = st[rr * 33 + lane] + (acc_in ? cbase[(long long)rr * sp.c_ld] : 0.f);
+            if (hbase) x *= dact(hbase[(long long)rr * sp.aux_ld]);
+            cbase[(long long)rr * sp.c_ld] = x;
           }
         }
+      };
+      switch (sp.act) {
+        case kActRelu: rows([](float h) { return h > 0.f ? 1.f : 0.f; }); break;
+        case kActElu: rows([](float h) { return h > 0.f ? 1.f : h + 1.f; }); break;
+        case kActTanh: rows([](float h) { return 1.f - h * h; }); break;
+        default: rows([](float) { return 1.f; }); break;
       }
     } else {
-      AdamScalars sc;
-      if (sp.P) sc = *sp.adam;
       const long long poff = (long long)g * sp.p_gs + (long long)row_base * sp.p_ld + col;
       float* cbase = sp.C ? sp.C + (long long)g * sp.c_gs + (long long)row_base * sp.c_ld + col : nullptr;
-      for (int r0 = 0; r0 < nrows; r0 += U) {
-        float pv[U], mv[U], vv[U];
-        if (sp.P) {
+      if (nrows == 32 && col_ok && sp.P) {  // full block: no per-element guards, 24 loads in flight per batch
+#pragma unroll 1
+        for (int r0 = 0; r0 < 32; r0 += U) {
+          float pv[U], mv[U], vv[U];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const bool ok = col_ok && r0 + u < nrows;
             const long long o = poff + (long long)(r0 + u) * sp.p_ld;
-            pv[u] = ok ? sp.P[o] : 0.f;
-            mv[u] = ok ? sp.M[o] : 0.f;
-            vv[u] = ok ? sp.V[o] : 0.f;
+            pv[u] = sp.P[o]; mv[u] = sp.M[o]; vv[u] = sp.V[o];
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const float gval = st[(r0 + u) * 33 + lane];
+            const long long o = poff + (long long)(r0 + u) * sp.p_ld;
+            adam_update(gval, pv[u], mv[u], vv[u], sc);
+            sp.P[o] = pv[u]; sp.M[o] = mv[u]; sp.V[o] = vv[u];
+            if (cbase) cbase[(long long)(r0 + u) * sp.c_ld] = gval;
           }
         }
+      } else {
+        for (int r0 = 0; r0 < nrows; r0 += U) {
+          float pv[U], mv[U], vv[U];
+          if (sp.P) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (col_ok && r0 + u < nrows) {
-            const float gval = st[(r0 + u) * 33 + lane];
-            if (sp.P) {
+            for (int u = 0; u < U; ++u) {
+              const bool ok = col_ok && r0 + u < nrows;
               const long long o = poff + (long long)(r0 + u) * sp.p_ld;
-              adam_update(gval, pv[u], mv[u], vv[u], sc);
-              sp.P[o] = pv[u];
-              sp.M[o] = mv[u];
-              sp.V[o] = vv[u];
+              pv[u] = ok ? sp.P[o] : 0.f;
+              mv[u] = ok ? sp.M[o] : 0.f;
+              vv[u] = ok ? sp.V[o] : 0.f;
             }
-            if (cbase) cbase[(long long)(r0 + u) * sp.c_ld] = gval;
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (col_ok && r0 + u < nrows) {
+              const float gval = st[(r0 + u) * 33 + lane];
+              if (sp.P) {
+                const long long o = poff + (long long)(r0 + u) * sp.p_ld;
+                adam_update(gval, pv[u], mv[u], vv[u], sc);
+                sp.P[o] = pv[u];
+                sp.M[o] = mv[u];
+                sp.V[o] = vv[u];
+              }
+              if (cbase) cbase[(long long)(r0 + u) * sp.c_ld] = gval;
+            }
           }
         }
       }
