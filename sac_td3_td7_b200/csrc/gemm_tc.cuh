@@ -334,33 +334,16 @@ __device__ __forceinline__ void tc_epilogue_warp(const GemmProblem& sp, int g, i
             if (cbase) cbase[(long long)(r0 + u) * sp.c_ld] = gval;
           }
         }
-      } else {
-        for (int r0 = 0; r0 < nrows; r0 += U) {
-          float pv[U], mv[U], vv[U];
+      } else if (col_ok) {  // ragged block or gradient-only problem: one row at a time
+        for (int rr = 0; rr < nrows; ++rr) {
+          const float gval = st[rr * 33 + lane];
           if (sp.P) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const bool ok = col_ok && r0 + u < nrows;
-              const long long o = poff + (long long)(r0 + u) * sp.p_ld;
-              pv[u] = ok ? sp.P[o] : 0.f;
-              mv[u] = ok ? sp.M[o] : 0.f;
-              vv[u] = ok ? sp.V[o] : 0.f;
-            }
+            const long long o = poff + (long long)rr * sp.p_ld;
+            float pv = sp.P[o], mv = sp.M[o], vv = sp.V[o];
+            adam_update(gval, pv, mv, vv, sc);
+            sp.P[o] = pv; sp.M[o] = mv; sp.V[o] = vv;
           }
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            if (col_ok && r0 + u < nrows) {
-              const float gval = st[(r0 + u) * 33 + lane];
-              if (sp.P) {
-                const long long o = poff + (long long)(r0 + u) * sp.p_ld;
-                adam_update(gval, pv[u], mv[u], vv[u], sc);
-                sp.P[o] = pv[u];
-                sp.M[o] = mv[u];
-                sp.V[o] = vv[u];
-              }
-              if (cbase) cbase[(long long)(r0 + u) * sp.c_ld] = gval;
-            }
-          }
+          if (cbase) cbase[(long long)rr * sp.c_ld] = gval;
         }
       }
     }
