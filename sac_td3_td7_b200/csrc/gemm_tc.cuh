@@ -211,6 +211,22 @@ struct TcOperand {
   }
 };
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// (out of line: its address arithmetic must not add to the register pressure of the epilogue proper)
+template <int MODE>
+__device__ __noinline__ void tc_prefetch_epilogue_operands(const GemmProblem& sp, int g, int prow, int pcol, int ncols) {
+  if (prow >= sp.I || pcol >= sp.J) return;
+  if (MODE == kWgrad && sp.P) {
+    const long long o = (long long)g * sp.p_gs + (long long)prow * sp.p_ld + pcol;
+    for (int c = 0; c < ncols && pcol + c < sp.J; c += 32) { prefetch_l2(sp.P + o + c); prefetch_l2(sp.M + o + c); prefetch_l2(sp.V + o + c); }
+  }
+  if (MODE == kDgrad && sp.aux) {
+    const long long o = (long long)g * sp.aux_gs + (long long)prow * sp.aux_ld + pcol;
+    for (int c = 0; c < ncols && pcol + c < sp.J; c += 32) prefetch_l2(sp.aux + o + c);
+  }
+}
+
 // Epilogue of one warp: its 32 output rows (TMEM lanes [32*rowgrp, +32) of the accumulator at `tmem_acc`) x the 128
 // columns starting at `colhalf`.  tcgen05.ld hands every thread one ROW (32 consecutive columns); going to global memory
 // like that would make each warp instruction touch 32 different rows.  So each 32x32 block is transposed through a padded
@@ -637,9 +653,15 @@ __global__ void __launch_bounds__(kWsThreads, 1) gemm_tc_ws_kernel(const __grid_
       decode(item, g, pi, i0);
       const GemmProblem& sp = L.p[pi];
       const unsigned a = n & 1, ause = n >> 1;
+      constexpr int kColsPerWarp = 256 / (kWsEpiWarps / 4);
+      // The epilogue's own global operands -- Adam's p / m / v (3 x 128 KB per tile: two thirds of the kernel's bytes) and
+      // the saved activations of a dgrad -- do not depend on the accumulator: their lines are requested into L2 here,
+      // before the wait for the MMAs, at no cost in registers (a warp's loads in flight are bounded by the registers that
+      // receive them: 24 per thread = 48 KB per SM, which kept the weight-gradient kernel latency-bound at 71 % of the HBM
+      // rate; from L2 the same loads return in a fraction of the DRAM latency).
+      if (MODE != kFwd) tc_prefetch_epilogue_operands<MODE>(sp, g, i0 + 32 * (warp & 3) + lane, (ew >> 2) * kColsPerWarp, kColsPerWarp);
       mbar_wait(&acc_full[a], ause & 1);
       tc_fence_after();
-      constexpr int kColsPerWarp = 256 / (kWsEpiWarps / 4);
       tc_epilogue_warp<MODE>(sp, g, sp.I, sp.J, (sp.J + 15) & ~15, i0, warp & 3, (ew >> 2) * kColsPerWarp, st, lane, tmem_base + a * 256u, 1, kColsPerWarp / 32);
       tc_fence_before();
       __syncwarp();
