@@ -532,14 +532,14 @@ def run_gpu_arm(args):
     hbm_peak, bf16_burst, bf16_sus, peak_src = measured_peaks()
     roofline, roof_extra = None, {}
     if seeds >= 8:
-        # dominant kernel of the stacked update (30 % of its kernel time, profiles/): persistent tcgen05 weight gradient + fused Adam
+        # dominant kernel of the stacked update (35 % of its kernel time, profiles/launches_td7_ant_pop256_r02.summary.txt): persistent tcgen05 weight gradient + fused Adam
         fl, by, ms3 = stacked_roofline(lib, torch, seeds, 2)
         ach = by / (ms3 * 1e-3) / 1e9
         roofline = {"kernel": f"gemm_tc_ws_kernel<wgrad> (persistent tcgen05 TF32, TMA-fed, fused Adam), 2 layers x {seeds} seeds", "bound": "hbm", "achieved": ach,
-                    "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": 1001.2e6, "launch_ms": ms3, "bytes_per_launch": by,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": 1009.6e6, "launch_ms": ms3, "bytes_per_launch": by,
                     "peak_source": peak_src + " (burst: kernel timed alone)",
                     "note": "algorithmic bytes per launch = 2 layers x seeds x 4 B x (dZ 256x256 + X 256x256 + p, m, v in and out 6 x 256x256), SURVEY 8(d) 24 B/param; "
-                            "traffic = dram__bytes_read + write of the same launch, profiles/gemm_tc_ws_mode2_ncu_full_r01.summary.txt",
+                            "traffic = dram__bytes_read + write of the same launch, profiles/gemm_tc_ws_mode2_ncu_full_r02.summary.txt (658.7 MB read + 350.9 MB written)",
                     "tensor": {"achieved": fl / (ms3 * 1e-3) / 1e12, "peak": bf16_sus, "unit": "TFLOP/s", "frac": fl / (ms3 * 1e-3) / 1e12 / bf16_sus}}
         fl0, by0, ms0 = stacked_roofline(lib, torch, seeds, 0)
         roof_extra["roofline_forward"] = {"kernel": "gemm_tc_ws_kernel<fwd>, 2 layers x %d seeds" % seeds, "bound": "hbm", "achieved": by0 / (ms0 * 1e-3) / 1e9, "peak": hbm_peak,
