@@ -151,8 +151,8 @@ struct GemmTable {
 // Narrow problems of a stacked-seed update (narrow.cuh): on wherever the tensor cores are (default), B200RL_NARROW=0
 // keeps them on the FFMA / tcgen05 kernels (A/B), B200RL_NARROW=1 forces them for any seed count (emulation tests).
 inline bool use_narrow(int groups) {
-  static const int env = [] { const char* e = getenv("B200RL_NARROW"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
-  return env >= 0 ? env != 0 : use_tensor_cores(groups);
+  const char* e = getenv("B200RL_NARROW");  // (read at every table build, like B200RL_TC: tests flip it inside one process)
+  return e ? atoi(e) != 0 : use_tensor_cores(groups);
 }
 
 // The small-tile kernel's product loop: fp32 FFMA (default), or error-compensated 3xTF32 on the warp-level tensor-core
