@@ -24,7 +24,7 @@ constexpr int kNwThreads = 256;  // output rows per CTA
 constexpr int kNwRows = 256;     // batch rows per pass (X staged whole: 32 KB)
 constexpr int kNwStageRows = 16; // rows of dZ per pipeline stage (16 KB)
 constexpr int kNwStages = 4;
-constexpr int kNwSmemBytes = (kNwRows * kNwCols + kNwStages * kNwStageRows * kNwThreads) * (int)sizeof(float);  // 96 KB: two CTAs per SM
+constexpr int kNwSmemBytes = (kNwRows * kNwCols + kNwStages * kNwStageRows * kNwThreads) * (int)sizeof(float);  // 96 KB: two CTAs per SM (8-row stages at three CTAs per SM were measured: 35 -> 43 us per 8-column problem)
 struct NarrowWgrad {
   const float* dZ; long long dz_gs; int dz_ld, rows, out;  // dZ [rows][out]
   const float* X; long long x_gs; int x_ld, J;             // X  [rows][J]
@@ -162,8 +162,9 @@ __global__ void __launch_bounds__(kNwThreads, 2) narrow_wgrad_kernel(const __gri
   if (L.dbg & 4) return;
   // ---- epilogue: the [256 rows][jn] gradient block goes through shared memory (row stride 33: conflict-free both ways)
   __syncthreads();  // everybody is done with the stages
-  float* G = Zs;
+  float* G = sm;  // (X and the stages are dead)
   constexpr int kGs = kNwCols + 1;
+  static_assert(kNwThreads * (kNwCols + 1) * (int)sizeof(float) <= kNwSmemBytes, "the gradient block must fit the kernel's shared memory");
   if (active) {
 #pragma unroll
     for (int a = 0; a < 4; ++a)
