@@ -23,6 +23,7 @@ namespace b200rl {
 
 constexpr int kActCluster = 8;
 constexpr int kActThreads = 256;
+#define ACT_PHASE_BARRIER(a) do { if ((a).dbg & 1) __syncthreads(); else { cluster_arrive(); cluster_wait(); } } while (0)
 
 struct ActLayer {
   const float* W;  // [out][ld] of stacked seed 0, bias right behind the layer as laid out by nets.cuh
@@ -39,6 +40,7 @@ struct ActArgs {
   float* out; long long out_gs;
   int pre_off[7];  // float offset (from the prefetch area) of this CTA's slice of layer l, -1: read from global memory
   int pre_total;   // floats of the prefetch area (0: no prefetch)
+  int dbg;         // measurement only (B200RL_ACT_DBG; results are wrong): bit 0 block barriers instead of cluster barriers, bit 1 no DSMEM pushes, bit 2 no weight loads
   unsigned* done;                    // device counter of finished CTAs (tag only)
   volatile unsigned long long* tag;  // written with tag_value once every seed's action is in `out` (null: none)
   unsigned long long tag_value;
@@ -59,7 +61,7 @@ __device__ __forceinline__ void st_cluster_f32(float* local, unsigned rank, floa
 // phase are in flight together.
 // Wsm != null: this CTA's rows [j_lo, j_hi) of W have been prefetched to shared memory (row stride ld).
 __device__ __forceinline__ void act_matvec(const ActLayer& Lr, int g, const float* xa, int na, const float* xb, int nb, int act, float* dst, float* gout, unsigned rank,
-                                           const ActLayer* L2r = nullptr, int act2 = 0, float* dst2 = nullptr, const float* Wsm = nullptr) {
+                                           const ActLayer* L2r = nullptr, int act2 = 0, float* dst2 = nullptr, const float* Wsm = nullptr, int dbg = 0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per = (Lr.out + kActCluster - 1) / kActCluster;
   const int j_lo = (int)rank * per, j_hi = min(Lr.out, j_lo + per);
@@ -92,7 +94,7 @@ __device__ __forceinline__ void act_matvec(const ActLayer& Lr, int g, const floa
           const float4 xv = *reinterpret_cast<const float4*>(x + k);
           float4 wv[4], wv2[4];
 #pragma unroll
-          for (int o = 0; o < 4; ++o) wv[o] = Wsm ? *reinterpret_cast<const float4*>(wr[o] + koff + k) : __ldg(reinterpret_cast<const float4*>(wr[o] + koff + k));
+          for (int o = 0; o < 4; ++o) wv[o] = (dbg & 4) ? make_float4(1.f, 1.f, 1.f, 1.f) : Wsm ? *reinterpret_cast<const float4*>(wr[o] + koff + k) : __ldg(reinterpret_cast<const float4*>(wr[o] + koff + k));
           if (W2) {
 #pragma unroll
             for (int o = 0; o < 4; ++o) wv2[o] = __ldg(reinterpret_cast<const float4*>(wr2[o] + koff + k));
@@ -125,11 +127,11 @@ __device__ __forceinline__ void act_matvec(const ActLayer& Lr, int g, const floa
     const int j = j0 + o_fin;
     if (j < j_hi) {
       const float y = act_forward((o_fin == 0 ? acc[0] : o_fin == 1 ? acc[1] : o_fin == 2 ? acc[2] : acc[3]) + bv, act);
-      if (dst) st_cluster_f32(dst + j, (unsigned)r_fin, y);
+      if (dst && !(dbg & 2)) st_cluster_f32(dst + j, (unsigned)r_fin, y);
       if (gout && r_fin == 0) gout[j] = y;
       if (W2) {
         const float y2 = act_forward((o_fin == 0 ? acc2[0] : o_fin == 1 ? acc2[1] : o_fin == 2 ? acc2[2] : acc2[3]) + bv2, act2);
-        st_cluster_f32(dst2 + j, (unsigned)r_fin, y2);
+        if (!(dbg & 2)) st_cluster_f32(dst2 + j, (unsigned)r_fin, y2);
       }
     }
   }
@@ -201,31 +203,31 @@ __global__ void __cluster_dims__(kActCluster, 1, 1) __launch_bounds__(kActThread
     }
     act_prefetch(a, 2, g, rank, wb); act_prefetch(a, 4, g, rank, wb); act_prefetch(a, 5, g, rank, wb); act_prefetch(a, 6, g, rank, wb);
     cp_async_wait<4>();  // (this thread's part of layer 1; the cluster barrier covers everybody's)
-    cluster_arrive(); cluster_wait();
-    act_matvec(a.L[1], g, v0, a.H, nullptr, 0, kActElu, v2, nullptr, rank, nullptr, 0, nullptr, wsm(1));   // h2 = elu(zs2 h1)
+    ACT_PHASE_BARRIER(a);
+    act_matvec(a.L[1], g, v0, a.H, nullptr, 0, kActElu, v2, nullptr, rank, nullptr, 0, nullptr, wsm(1), a.dbg);   // h2 = elu(zs2 h1)
     act_norm(v1, a.H, red);                                                   // p0n (local copy; nobody writes v1 any more)
     cp_async_wait<3>();
-    cluster_arrive(); cluster_wait();
-    act_matvec(a.L[2], g, v2, a.H, nullptr, 0, kActNone, v3, nullptr, rank, nullptr, 0, nullptr, wsm(2));  // u3 = zs3 h2
+    ACT_PHASE_BARRIER(a);
+    act_matvec(a.L[2], g, v2, a.H, nullptr, 0, kActNone, v3, nullptr, rank, nullptr, 0, nullptr, wsm(2), a.dbg);  // u3 = zs3 h2
     cp_async_wait<2>();
-    cluster_arrive(); cluster_wait();
+    ACT_PHASE_BARRIER(a);
     act_norm(v3, a.Z, red);                                                   // zs
-    act_matvec(a.L[4], g, v1, a.H, v3, a.Z, kActRelu, v0, nullptr, rank, nullptr, 0, nullptr, wsm(4));     // a1 = relu(l1 [p0n, zs])
+    act_matvec(a.L[4], g, v1, a.H, v3, a.Z, kActRelu, v0, nullptr, rank, nullptr, 0, nullptr, wsm(4), a.dbg);     // a1 = relu(l1 [p0n, zs])
     cp_async_wait<1>();
-    cluster_arrive(); cluster_wait();
-    act_matvec(a.L[5], g, v0, a.H, nullptr, 0, kActRelu, v2, nullptr, rank, nullptr, 0, nullptr, wsm(5));  // a2 = relu(l2 a1)
+    ACT_PHASE_BARRIER(a);
+    act_matvec(a.L[5], g, v0, a.H, nullptr, 0, kActRelu, v2, nullptr, rank, nullptr, 0, nullptr, wsm(5), a.dbg);  // a2 = relu(l2 a1)
     cp_async_wait<0>();
-    cluster_arrive(); cluster_wait();
-    act_matvec(a.L[6], g, v2, a.H, nullptr, 0, kActTanh, nullptr, out, rank, nullptr, 0, nullptr, wsm(6));  // a = tanh(l3 a2)
+    ACT_PHASE_BARRIER(a);
+    act_matvec(a.L[6], g, v2, a.H, nullptr, 0, kActTanh, nullptr, out, rank, nullptr, 0, nullptr, wsm(6), a.dbg);  // a = tanh(l3 a2)
   } else {
     act_matvec(a.L[0], g, xo, a.S, nullptr, 0, kActRelu, v0, nullptr, rank);
     act_prefetch(a, 2, g, rank, wb);
     cp_async_wait<1>();
-    cluster_arrive(); cluster_wait();
-    act_matvec(a.L[1], g, v0, a.H, nullptr, 0, kActRelu, v1, nullptr, rank, nullptr, 0, nullptr, wsm(1));
+    ACT_PHASE_BARRIER(a);
+    act_matvec(a.L[1], g, v0, a.H, nullptr, 0, kActRelu, v1, nullptr, rank, nullptr, 0, nullptr, wsm(1), a.dbg);
     cp_async_wait<0>();
-    cluster_arrive(); cluster_wait();
-    act_matvec(a.L[2], g, v1, a.H, nullptr, 0, a.kind == 1 ? kActTanh : kActNone, nullptr, out, rank, nullptr, 0, nullptr, wsm(2));
+    ACT_PHASE_BARRIER(a);
+    act_matvec(a.L[2], g, v1, a.H, nullptr, 0, a.kind == 1 ? kActTanh : kActNone, nullptr, out, rank, nullptr, 0, nullptr, wsm(2), a.dbg);
   }
   if (a.tag && a.total_ctas == (unsigned)kActCluster) {  // one seed: the cluster barrier orders the eight CTAs' stores, CTA 0 posts the tag
     __syncthreads();

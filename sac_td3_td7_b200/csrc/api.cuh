@@ -335,6 +335,7 @@ static int build_act_path(b200rl_agent* h) {
       tot = 0;
     }
     aa.pre_total = (int)tot;
+    if (const char* e = getenv("B200RL_ACT_DBG")) aa.dbg = atoi(e);
   }
   h->act_smem = (int)((round_up(S, 4) + 4ll * aa.vmax + aa.pre_total) * sizeof(float));
   B200_REQUIRE(h->act_smem <= 200 * 1024, "acting path: observation / hidden sizes too large for the fused kernel");
