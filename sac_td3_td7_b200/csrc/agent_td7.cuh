@@ -47,6 +47,13 @@ struct TD7Agent : AgentBase {
   GemmTable We[6];         // encoder weight gradients (+Adam), one launch per layer
   GemmTable Cq[3];         // one agent: the current critics' forward q1 q2 q3 as a branch of its own (split_q)
   bool split_q = false;
+  // stacked seeds on the tensor cores: every AvgL1Norm rides in the epilogue of the layer that produces its input (kActNorm),
+  // the six normalisation launches of an update (each a full pass over 67-134 MB at 256 seeds) are not issued
+  bool fuse_norm = false;
+  static GemmProblem with_norm(GemmProblem pr, const Mat& y) {
+    pr.act = kActNorm; pr.aux = y.p; pr.aux_ld = y.ld; pr.aux_gs = y.gs;
+    return pr;
+  }
   GemmTable C2v[2];        // second launch of the critic chain, without / with the actor step's l0(s)
   GemmTable Wq[4], Wp[4];  // critic / policy weight gradients (+Adam), one launch per layer: [0] = last layer
   RowTable En[2], Cn[4], An[4];
@@ -134,10 +141,12 @@ struct TD7Agent : AgentBase {
     const Mat s_all = ss, s_cur = ss.rows_from(0, B), s_nxt = ss.rows_from(B, B);
     const Mat z_cur = e_z.rows_from(0, B), z_nxt = e_z.rows_from(B, B);
     const float sigma = (float)cfg.target_policy_noise, clipv = (float)cfg.noise_clip;
+    fuse_norm = use_tensor_cores(G);
+    auto nrm = [&](GemmProblem pr, const Mat& y) { return fuse_norm ? with_norm(pr, y) : pr; };
     // ------------------------------------------------ encoder branch (td7.py:246-257, 299-303)
     B200_TRY(up(E[0], kFwd, PV{fwd_problem(enc, 0, {s_all}, e_h1, kActElu)}, true));
     B200_TRY(up(E[1], kFwd, PV{fwd_problem(enc, 1, {e_h1}, e_h2, kActElu)}, true));
-    B200_TRY(up(E[2], kFwd, PV{fwd_problem(enc, 2, {e_h2}, e_u3, kActNone)}, true));
+    B200_TRY(up(E[2], kFwd, PV{nrm(fwd_problem(enc, 2, {e_h2}, e_u3, kActNone), e_z)}, true));
     B200_TRY(upn(En[0], false, {nf(e_u3, e_z)}));
     B200_TRY(up(E[3], kFwd, PV{fwd_problem(enc, 3, {z_cur, act_in}, e_g1, kActElu)}, true));
     B200_TRY(up(E[4], kFwd, PV{fwd_problem(enc, 4, {e_g1}, e_g2, kActElu)}, true));
@@ -167,17 +176,17 @@ struct TD7Agent : AgentBase {
     // ------------------------------------------------ critic chain (td7.py:175-244, 307-315)
     // first launch: 4 x 64 tiles = one wave at 2 CTAs per SM; the policy's l0 rides with the second launch (128 tiles)
     B200_TRY(up(C[0], kFwd, PV{fwd_problem(fet, 0, {s_nxt}, t1, kActElu), fwd_problem(fe, 0, {s_cur}, f1, kActElu),
-                               fwd_problem(q[0], 0, {s_cur, act_in}, cq0[0], kActNone), fwd_problem(q[1], 0, {s_cur, act_in}, cq0[1], kActNone)}));
+                               nrm(fwd_problem(q[0], 0, {s_cur, act_in}, cq0[0], kActNone), cq0n[0]), nrm(fwd_problem(q[1], 0, {s_cur, act_in}, cq0[1], kActNone), cq0n[1])}));
     B200_TRY(upn(CnQ, false, {nf(cq0[0], cq0n[0]), nf(cq0[1], cq0n[1])}));
     {
-      PV c2{fwd_problem(fet, 1, {t1}, t2, kActElu), fwd_problem(fe, 1, {f1}, f2, kActElu), fwd_problem(pol, 0, {s_nxt}, pa0, kActNone)};
+      PV c2{fwd_problem(fet, 1, {t1}, t2, kActElu), fwd_problem(fe, 1, {f1}, f2, kActElu), nrm(fwd_problem(pol, 0, {s_nxt}, pa0, kActNone), pa0n)};
       B200_TRY(up(C2v[0], kFwd, c2));
-      c2.push_back(fwd_problem(pol, 0, {s_cur}, pb0, kActNone));  // actor steps also need l0(s)
+      c2.push_back(nrm(fwd_problem(pol, 0, {s_cur}, pb0, kActNone), pb0n));  // actor steps also need l0(s)
       B200_TRY(up(C2v[1], kFwd, c2));
     }
     B200_TRY(upn(CnP[0], false, {nf(pa0, pa0n)}));
     B200_TRY(upn(CnP[1], false, {nf(pa0, pa0n), nf(pb0, pb0n)}));
-    B200_TRY(up(C[3], kFwd, PV{fwd_problem(fet, 2, {t2}, tu3, kActNone), fwd_problem(fe, 2, {f2}, fu3, kActNone)}));
+    B200_TRY(up(C[3], kFwd, PV{nrm(fwd_problem(fet, 2, {t2}, tu3, kActNone), zs_t), nrm(fwd_problem(fe, 2, {f2}, fu3, kActNone), zs_f)}));
     B200_TRY(upn(Cn[2], false, {nf(tu3, zs_t), nf(fu3, zs_f)}));
     B200_TRY(up(C[4], kFwd, PV{fwd_problem(pol, 1, {pa0n, zs_t}, p1, kActRelu), fwd_problem(fe, 3, {zs_f, act_in}, fa1, kActElu)}));
     B200_TRY(up(C[5], kFwd, PV{fwd_problem(pol, 2, {p1}, p2, kActRelu), fwd_problem(fe, 4, {fa1}, fa2, kActElu)}));
@@ -192,16 +201,16 @@ struct TD7Agent : AgentBase {
     // fill the machine either way and keep the grouped launches.
     split_q = (G == 1);
     if (split_q) {
-      B200_TRY(up(C[7], kFwd, PV{fwd_problem(fet, 3, {zs_t, a_next}, ta1, kActElu), fwd_problem(qt[0], 0, {s_nxt, a_next}, tq0[0], kActNone),
-                                 fwd_problem(qt[1], 0, {s_nxt, a_next}, tq0[1], kActNone)}));
+      B200_TRY(up(C[7], kFwd, PV{fwd_problem(fet, 3, {zs_t, a_next}, ta1, kActElu), nrm(fwd_problem(qt[0], 0, {s_nxt, a_next}, tq0[0], kActNone), tq0n[0]),
+                                 nrm(fwd_problem(qt[1], 0, {s_nxt, a_next}, tq0[1], kActNone), tq0n[1])}));
       B200_TRY(up(C[8], kFwd, PV{fwd_problem(fet, 4, {ta1}, ta2, kActElu)}));
       B200_TRY(up(C[9], kFwd, PV{fwd_problem(fet, 5, {ta2}, zsa_t, kActNone)}));
       B200_TRY(up(Cq[0], kFwd, PV{fwd_problem(q[0], 1, {cq0n[0], zsa_f, zs_f}, cqa[0], kActElu), fwd_problem(q[1], 1, {cq0n[1], zsa_f, zs_f}, cqa[1], kActElu)}, true));
       B200_TRY(up(Cq[1], kFwd, PV{fwd_problem(q[0], 2, {cqa[0]}, cqb[0], kActElu), fwd_problem(q[1], 2, {cqa[1]}, cqb[1], kActElu)}, true));
       B200_TRY(up(Cq[2], kFwd, PV{fwd_problem(q[0], 3, {cqb[0]}, qv[0], kActNone), fwd_problem(q[1], 3, {cqb[1]}, qv[1], kActNone)}, true));
     } else {
-      B200_TRY(up(C[7], kFwd, PV{fwd_problem(fet, 3, {zs_t, a_next}, ta1, kActElu), fwd_problem(qt[0], 0, {s_nxt, a_next}, tq0[0], kActNone),
-                                 fwd_problem(qt[1], 0, {s_nxt, a_next}, tq0[1], kActNone), fwd_problem(q[0], 1, {cq0n[0], zsa_f, zs_f}, cqa[0], kActElu),
+      B200_TRY(up(C[7], kFwd, PV{fwd_problem(fet, 3, {zs_t, a_next}, ta1, kActElu), nrm(fwd_problem(qt[0], 0, {s_nxt, a_next}, tq0[0], kActNone), tq0n[0]),
+                                 nrm(fwd_problem(qt[1], 0, {s_nxt, a_next}, tq0[1], kActNone), tq0n[1]), fwd_problem(q[0], 1, {cq0n[0], zsa_f, zs_f}, cqa[0], kActElu),
                                  fwd_problem(q[1], 1, {cq0n[1], zsa_f, zs_f}, cqa[1], kActElu)}));
       B200_TRY(up(C[8], kFwd, PV{fwd_problem(fet, 4, {ta1}, ta2, kActElu), fwd_problem(q[0], 2, {cqa[0]}, cqb[0], kActElu), fwd_problem(q[1], 2, {cqa[1]}, cqb[1], kActElu)}));
       B200_TRY(up(C[9], kFwd, PV{fwd_problem(fet, 5, {ta2}, zsa_t, kActNone), fwd_problem(q[0], 3, {cqb[0]}, qv[0], kActNone), fwd_problem(q[1], 3, {cqb[1]}, qv[1], kActNone)}));
@@ -237,7 +246,7 @@ struct TD7Agent : AgentBase {
     B200_TRY(up(Aa[3], kFwd, PV{fwd_problem(fe, 3, {zs_f, a_pi}, pa1, kActElu)}, true));
     B200_TRY(up(Aa[4], kFwd, PV{fwd_problem(fe, 4, {pa1}, pa2, kActElu)}, true));
     B200_TRY(up(Aa[5], kFwd, PV{fwd_problem(fe, 5, {pa2}, zsa_pi, kActNone)}, true));
-    B200_TRY(up(Aa[6], kFwd, PV{fwd_problem(q[0], 0, {s_cur, a_pi}, aq0[0], kActNone), fwd_problem(q[1], 0, {s_cur, a_pi}, aq0[1], kActNone)}));
+    B200_TRY(up(Aa[6], kFwd, PV{nrm(fwd_problem(q[0], 0, {s_cur, a_pi}, aq0[0], kActNone), aq0n[0]), nrm(fwd_problem(q[1], 0, {s_cur, a_pi}, aq0[1], kActNone), aq0n[1])}));
     B200_TRY(upn(An[0], false, {nf(aq0[0], aq0n[0]), nf(aq0[1], aq0n[1])}));
     B200_TRY(up(Aa[7], kFwd, PV{fwd_problem(q[0], 1, {aq0n[0], zsa_pi, zs_f}, aqa[0], kActElu), fwd_problem(q[1], 1, {aq0n[1], zsa_pi, zs_f}, aqa[1], kActElu)}));
     B200_TRY(up(Aa[8], kFwd, PV{fwd_problem(q[0], 2, {aqa[0]}, aqb[0], kActElu), fwd_problem(q[1], 2, {aqa[1]}, aqb[1], kActElu)}));
@@ -359,6 +368,7 @@ struct TD7Agent : AgentBase {
 
 #define GL(tbl, st) B200_TRY(gemm_table_launch(tbl, G, st))
 #define RL(tbl, st) B200_TRY(row_table_launch(tbl, G, st))
+#define RLF(tbl, st) do { if (!fuse_norm) RL(tbl, st); } while (0)  // forward AvgL1Norm: fused into its producer on the tensor-core path
 
   int launch_enc_loss(cudaStream_t s) {
     dim3 grid((unsigned)ceil_div(B, 8), (unsigned)G), block(256);
@@ -409,18 +419,18 @@ struct TD7Agent : AgentBase {
     GL(C[0], M);
     // ---- encoder branch
     B200_TRY(fork.link(M, sE));
-    GL(E[0], sE); GL(E[1], sE); GL(E[2], sE); RL(En[0], sE);
+    GL(E[0], sE); GL(E[1], sE); GL(E[2], sE); RLF(En[0], sE);
     GL(E[3], sE); GL(E[4], sE); GL(E[5], sE);
     B200_TRY(fork.link(sP, sE));  // info slot (loss) and Adam scalars (wgrad)
     B200_TRY(launch_enc_loss(sE));
     GL(E[6], sE); GL(We[5], sE); GL(E[7], sE); GL(We[4], sE); GL(E[8], sE); GL(We[3], sE); RL(En[1], sE);
     GL(E[9], sE); GL(We[2], sE); GL(E[10], sE); GL(We[1], sE); GL(We[0], sE);
     B200_TRY(fork.link(M, sN));
-    RL(CnQ, sN);
+    RLF(CnQ, sN);
     GL(C2v[actor ? 1 : 0], M);
     B200_TRY(fork.link(M, sN));
-    RL(CnP[actor ? 1 : 0], sN);
-    GL(C[3], M); RL(Cn[2], M);
+    RLF(CnP[actor ? 1 : 0], sN);
+    GL(C[3], M); RLF(Cn[2], M);
     B200_TRY(fork.link(sN, M));
     if (actor) {  // hoisted part of the actor step: needs zs_f, pb0n, the (unchanged) policy and fixed encoder
       B200_TRY(fork.link(M, sA));
@@ -435,7 +445,7 @@ struct TD7Agent : AgentBase {
     }
     GL(C[7], M);
     B200_TRY(fork.link(M, sN));
-    RL(Cn[3], sN);
+    RLF(Cn[3], sN);
     GL(C[8], M); GL(C[9], M);
     B200_TRY(fork.link(sN, M));
     GL(C[10], M); GL(C[11], M); GL(C[12], M);
@@ -456,7 +466,7 @@ struct TD7Agent : AgentBase {
     if (!actor) B200_TRY(fork.link(sN, M));
     if (actor) {
       B200_TRY(fork.link(sA, M));
-      GL(Aa[6], M); RL(An[0], M);   // q01 was just updated on this stream; the deeper critic layers are still being
+      GL(Aa[6], M); RLF(An[0], M);   // q01 was just updated on this stream; the deeper critic layers are still being
       B200_TRY(fork.link(sN, M));   // updated on sN: joined only where the new q1 weights are first read
       GL(Aa[7], M); GL(Aa[8], M);
       B200_TRY(fork.link(M, sN));
@@ -528,6 +538,7 @@ struct TD7Agent : AgentBase {
 
 #undef GL
 #undef RL
+#undef RLF
 };
 
 }  // namespace b200rl

@@ -47,7 +47,10 @@
 namespace b200rl {
 
 enum GemmMode : int { kFwd = 0, kDgrad = 1, kWgrad = 2 };
-enum Act : int { kActNone = 0, kActRelu = 1, kActElu = 2, kActTanh = 3, kActTanhNoise = 4 };
+enum Act : int { kActNone = 0, kActRelu = 1, kActElu = 2, kActTanh = 3, kActTanhNoise = 4,
+                 // forward, tensor-core path only: C = x (bias added, no activation) AND aux = AvgL1Norm(x) = x / max(mean|x|, 1e-8)
+                 // over the J columns of each row (rl/nn/sale.py:11-13) -- the normalisation fused into the producing layer
+                 kActNorm = 5 };
 
 // Adam scalars for one optimizer, refreshed on device once per update by `prep_step_kernel`
 // (float casts of the Python doubles torch computes in `_single_tensor_adam`).

@@ -232,12 +232,42 @@ __device__ __noinline__ void tc_prefetch_epilogue_operands(const GemmProblem& sp
 // like that would make each warp instruction touch 32 different rows.  So each 32x32 block is transposed through a padded
 // shared-memory tile `st` (32 x 33 floats, private to the warp) and written row by row with lane = column: every global
 // access of the epilogue -- C, bias, aux, and Adam's p/m/v -- is a coalesced 128-byte line.
+// Fused AvgL1Norm (act == kActNorm): the warps that share a row group (`nshare` of them, this one is number `qidx`) first
+// add up |x| of their columns straight from TMEM (thread = row), meet at a named barrier, and every thread then knows
+// its row's mean; the second pass is the ordinary transposed write, of x and of x / max(mean|x|, eps).  `nred`:
+// [2][4][4][32] floats of shared memory (double-buffered by `parity`: a fast warp may start the next tile while a slow one
+// still reads this tile's sums), `ncs`: 32 floats private to the warp.
 template <int MODE>
 __device__ __forceinline__ void tc_epilogue_warp(const GemmProblem& sp, int g, int I, int J, int n_pad, int i0, int rowgrp, int colhalf, float* st, int lane,
-                                                 uint32_t tmem_acc, int total_chunks, int ncb = 4) {
+                                                 uint32_t tmem_acc, int total_chunks, int ncb = 4, float* nred = nullptr, float* ncs = nullptr, int nshare = 1,
+                                                 int qidx = 0, unsigned parity = 0) {
   const int row_base = i0 + 32 * rowgrp;
   AdamScalars sc = {};
   if (MODE == kWgrad && sp.P) sc = *sp.adam;  // (once per tile, its round trip behind the accumulator wait of the first block)
+  const bool fused_norm = (MODE == kFwd) && sp.act == kActNorm;
+  if (fused_norm) {
+    float part = 0.f;
+#pragma unroll 1
+    for (int cc = 0; cc < ncb; ++cc) {
+      const int col0 = colhalf + cc * 32;
+      if (col0 >= n_pad) break;
+      st[lane] = (sp.bias && col0 + lane < J) ? sp.bias[(long long)g * sp.bias_gs + col0 + lane] : 0.f;
+      __syncwarp();
+      float v[32];
+      tc_ld32(tmem_acc + ((uint32_t)(32 * rowgrp) << 16) + (uint32_t)col0, v);
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        if (col0 + e < J) part += fabsf((total_chunks > 0 ? v[e] : 0.f) + st[e]);
+      __syncwarp();
+    }
+    float* slot = nred + ((parity * 4 + rowgrp) * 4) * 32;
+    slot[qidx * 32 + lane] = part;
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + rowgrp), "r"(32 * nshare) : "memory");
+    float tot = 0.f;
+    for (int q = 0; q < nshare; ++q) tot += slot[q * 32 + lane];
+    ncs[lane] = fmaxf(tot / (float)J, 1e-8f);
+    __syncwarp();
+  }
 #pragma unroll 1
   for (int cc = 0; cc < ncb; ++cc) {
     const int col0 = colhalf + cc * 32;
@@ -284,6 +314,22 @@ __device__ __forceinline__ void tc_epilogue_warp(const GemmProblem& sp, int g, i
             for (int rr = 0; rr < nrows; ++rr) cptr[(long long)rr * ld] = f(st[rr * 33 + lane] + bias);
           }
         };
+        if (fused_norm) {
+          float* yptr = const_cast<float*>(sp.aux) + (long long)g * sp.aux_gs + (long long)row_base * sp.aux_ld + col;
+          const long long ldy = sp.aux_ld;
+          for (int r0 = 0; r0 < nrows; r0 += 8) {
+            float x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x[u] = (r0 + u < nrows) ? st[(r0 + u) * 33 + lane] + bias : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              if (r0 + u < nrows) {
+                cptr[(long long)(r0 + u) * ld] = x[u];
+                yptr[(long long)(r0 + u) * ldy] = x[u] / ncs[r0 + u];
+              }
+            }
+          }
+        } else
         switch (sp.act) {
           case kActRelu: rows([](float v) { return v > 0.f ? v : 0.f; }); break;
           case kActElu: rows([](float v) { return v > 0.f ? v : __expf(v) - 1.f; }); break;
@@ -522,7 +568,10 @@ __global__ void __launch_bounds__(kTcThreads, 2) gemm_tc_kernel(const __grid_con
 
   // ---- epilogue: warp w owns rows [32*(w&3), +32) and columns [128*(w>>2), +128); the pipeline stages are free now
   // and serve as the warps' transposition tiles ----
-  tc_epilogue_warp<MODE>(sp, g, I, J, n_pad, i0, warp & 3, (warp >> 2) * 128, reinterpret_cast<float*>(smem) + warp * (32 * 33), lane, tmem_base, total_chunks);
+  __shared__ float s_nred[2 * 4 * 4 * 32];
+  __shared__ float s_ncs[(kTcThreads / 32) * 32];
+  tc_epilogue_warp<MODE>(sp, g, I, J, n_pad, i0, warp & 3, (warp >> 2) * 128, reinterpret_cast<float*>(smem) + warp * (32 * 33), lane, tmem_base, total_chunks, 4,
+                         s_nred, s_ncs + warp * 32, kTcThreads / 128, warp >> 2, 0u);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -551,6 +600,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 template <int MODE>
 __global__ void __launch_bounds__(kWsThreads, 1) gemm_tc_ws_kernel(const __grid_constant__ GemmLaunch L, int groups) {
+  __shared__ float s_nred[2 * 4 * 4 * 32];  // fused AvgL1Norm: partial row sums of the column groups (tc_epilogue_warp)
+  __shared__ float s_ncs[kWsEpiWarps * 32];
   B200_PDL_PROLOGUE();
   constexpr bool A_KM = (MODE != kWgrad);
   constexpr bool B_KM = (MODE == kFwd);
@@ -662,7 +713,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) gemm_tc_ws_kernel(const __grid_
       if (MODE != kFwd) tc_prefetch_epilogue_operands<MODE>(sp, g, i0 + 32 * (warp & 3) + lane, (ew >> 2) * kColsPerWarp, kColsPerWarp);
       mbar_wait(&acc_full[a], ause & 1);
       tc_fence_after();
-      tc_epilogue_warp<MODE>(sp, g, sp.I, sp.J, (sp.J + 15) & ~15, i0, warp & 3, (ew >> 2) * kColsPerWarp, st, lane, tmem_base + a * 256u, 1, kColsPerWarp / 32);
+      tc_epilogue_warp<MODE>(sp, g, sp.I, sp.J, (sp.J + 15) & ~15, i0, warp & 3, (ew >> 2) * kColsPerWarp, st, lane, tmem_base + a * 256u, 1, kColsPerWarp / 32,
+                             s_nred, s_ncs + ew * 32, kWsEpiWarps / 4, ew >> 2, n & 1u);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[a]);

@@ -229,6 +229,15 @@ inline int gemm_table_upload(GemmTable* t, int mode, std::vector<GemmProblem>& p
   for (auto& p : probs) {
     B200_REQUIRE(p.nseg >= 1 && p.nseg <= 3, "gemm problem needs 1..3 segments");
     B200_REQUIRE(p.I > 0 && p.J > 0, "gemm problem with empty output");
+    if (p.act == kActNorm) {
+      bool ok = (mode == kFwd) && want_tc && p.aux != nullptr;
+#ifndef B200_EMU
+      ok = ok && tc_eligible(p);
+#else
+      ok = false;
+#endif
+      B200_REQUIRE(ok, "a fused AvgL1Norm epilogue exists on the tensor-core forward path only (128-row tiles, 64..256 columns)");
+    }
     if (want_narrow && rank1_eligible(p, mode)) { r1.push_back(p); continue; }
 #ifndef B200_EMU
     if (want_tc && tc_eligible(p)) { tc.push_back(p); continue; }

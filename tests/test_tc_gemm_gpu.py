@@ -217,3 +217,33 @@ def test_wgrad_with_a_non_tileable_input_width_is_cut_into_column_blocks(tc):
         wt.grad = torch.tensor(g[s])
         opt.step()
         assert np.abs(out[s] - wt.detach().numpy()).max() <= 2e-7
+
+
+@pytest.mark.parametrize("G,M,N,K", [(3, 256, 256, 256), (2, 512, 256, 27), (1, 128, 64, 40)])
+def test_tc_forward_with_fused_avgl1norm(tc, G, M, N, K):
+    """act = 5 (kActNorm): C = x W^T + b and aux = AvgL1Norm(C) = C / max(mean|C|, 1e-8) per row (rl/nn/sale.py:11-13), the
+    normalisation done in the epilogue of the producing layer by the warps that share a row group."""
+    dev = tc
+    rng = np.random.default_rng(G * 1000 + K)
+    ld = (K + 3) // 4 * 4
+    x = np.zeros((G, M, ld), np.float32)
+    x[:, :, :K] = rng.standard_normal((G, M, K))
+    W = np.zeros((G, N, ld), np.float32)
+    W[:, :, :K] = rng.standard_normal((G, N, K)) / np.sqrt(K)
+    b = rng.standard_normal((G, N)).astype(np.float32)
+    y, yn = dev.zeros((G, M, N)), dev.zeros((G, M, N))
+    p = _problem(M, N, y, N)
+    _seg(p, dev.to_dev(x), ld, dev.to_dev(W), ld, K)
+    p.seg[0].a_gs, p.seg[0].b_gs, p.c_gs = M * ld, N * ld, M * N
+    p.bias, p.bias_gs, p.act = dev.to_dev(b), N, 5
+    p.aux, p.aux_ld, p.aux_gs = yn, N, M * N
+    _run(dev, 0, [p], groups=G)
+    got, gotn = dev.from_dev(y, (G, M, N)), dev.from_dev(yn, (G, M, N))
+    for s in range(G):
+        ref = F.linear(torch.tensor(x[s, :, :K]), torch.tensor(W[s, :, :K]), torch.tensor(b[s]))
+        refn = ref / ref.abs().mean(-1, keepdim=True).clamp(min=1e-8)
+        assert nerr(got[s], ref.numpy()) < TOL
+        assert nerr(gotn[s], refn.numpy()) < TOL
+        # the normalised output is exactly the kernel's own pre-norm output over its row mean
+        own = got[s] / np.maximum(np.abs(got[s]).mean(-1, keepdims=True), 1e-8)
+        assert nerr(gotn[s], own) < 2e-6
