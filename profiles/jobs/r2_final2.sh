@@ -12,11 +12,16 @@ for w in ("td7_ant_pop256", "td7_humanoid_pop256"):
     agent, buf = bench.make_agent_and_buffer(w, 0)
     infos = agent.train_ops_n(1500, buf)
     torch.cuda.synchronize()
-    last = agent.info_dicts(agent.n_runs - 8, 8) if hasattr(agent, "info_dicts") else infos[-8:]
-    vals = np.array([[float(v) for v in d.values() if v is not None] for d in (last if isinstance(last, list) else [last])], dtype=np.float64)
-    pr = buf.priority
-    ok = np.isfinite(vals).all() and bool(torch.isfinite(pr).all())
-    print(w, "1500 stacked updates: losses finite", bool(np.isfinite(vals).all()), "priorities finite", bool(torch.isfinite(pr).all()), "max_priority", float(torch.as_tensor(buf.max_priority).max()), "q_fn tail", vals[-1][:3])
+    q = float(infos[-1]["train/q_fn"])
+    from sac_td3_td7_b200 import _lib
+    n = buf.replay_buffer_size
+    out = np.empty(n, np.float32)
+    ok, mx = np.isfinite(q), 0.0
+    for g in (0, 1, 100, 255):  # a NaN anywhere in a seed's critic poisons that seed's priorities
+        _lib.check(buf._lib.b200rl_replay_read_priority(buf._h, g, 0, n, out.ctypes.data, _lib.current_stream_ptr()))
+        ok = ok and bool(np.isfinite(out).all()) and float(out.max()) < 1e6
+        mx = max(mx, float(out.max()))
+    print(w, "1500 stacked updates (384 k agent-updates): seed-0 critic loss", q, "| priorities of seeds 0/1/100/255 finite and bounded:", bool(ok), "max", mx)
     assert ok
     del agent, buf
     torch.cuda.empty_cache()
