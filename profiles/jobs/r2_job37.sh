@@ -1,0 +1,3 @@
+cd /root/repo
+timeout 900 python -m pytest tests/test_population_gpu.py tests/test_agent_parity.py -m gpu -q 2>&1 | tail -4 | cut -c1-300
+for w in td7_ant_pop256; do timeout 300 python profiles/prof_update.py $w 8 2>&1 | tail -1; done

@@ -141,7 +141,8 @@ struct TD7Agent : AgentBase {
     const Mat s_all = ss, s_cur = ss.rows_from(0, B), s_nxt = ss.rows_from(B, B);
     const Mat z_cur = e_z.rows_from(0, B), z_nxt = e_z.rows_from(B, B);
     const float sigma = (float)cfg.target_policy_noise, clipv = (float)cfg.noise_clip;
-    fuse_norm = use_tensor_cores(G);
+    // (only where every producing layer is a tensor-core problem: 128-row tiles, 64..256 columns in steps of 16)
+    fuse_norm = use_tensor_cores(G) && (B % 128) == 0 && H >= 64 && H <= 256 && (H % 16) == 0 && Z >= 64 && Z <= 256 && (Z % 16) == 0;
     auto nrm = [&](GemmProblem pr, const Mat& y) { return fuse_norm ? with_norm(pr, y) : pr; };
     // ------------------------------------------------ encoder branch (td7.py:246-257, 299-303)
     B200_TRY(up(E[0], kFwd, PV{fwd_problem(enc, 0, {s_all}, e_h1, kActElu)}, true));

@@ -330,3 +330,23 @@ def test_population_evaluate_hook_batches_acting_over_seeds():
                 total += r
                 done = term or trunc
         assert abs(ret[g] - total / 2) <= 1e-4
+
+
+@pytest.mark.parametrize("batch,hdim", [(96, 256), (256, 200)])
+def test_stacked_seeds_with_shapes_the_tensor_cores_cannot_tile(batch, hdim):
+    """A batch that is not a multiple of 128 rows, or a hidden width that is not a multiple of 16, keeps a stacked population
+    off the tcgen05 kernels (and off the fused AvgL1Norm epilogue): the fp32 kernels take over, the update still runs and every
+    seed's losses are finite and distinct."""
+    from sac_td3_td7_b200.rl.agent import TD7
+    from sac_td3_td7_b200.rl.replay_memory import LAPReplayMemory
+
+    G = 8
+    torch.manual_seed(3)
+    agent = TD7("Hopper-v4", use_lap=True, n_seeds=G, batch_size=batch, hdim=hdim, zs_dim=hdim)
+    agent.seed_population(11)
+    buf = LAPReplayMemory(4096, "Hopper-v4", n_seeds=G)
+    buf.fill_synthetic(4000, seed=2)
+    agent.train_ops_n(6, buf)
+    torch.cuda.synchronize()
+    q = np.array([agent.info_dicts(agent.n_runs, 1, seed=g)[0]["train/q_fn"] for g in range(G)], np.float64)
+    assert np.isfinite(q).all() and len(set(np.round(q, 6))) == G
