@@ -335,6 +335,8 @@ def e2e_loop(agent, buf, steps, W, world, total_seeds, dist=None):
 
     for i in range(W):
         step(i)
+    if dist is not None:  # (the first collective of a shape sets up its NCCL channels: part of the warm-up, like the graph capture)
+        gather_per_seed(torch.zeros(G, device="cuda"), total_seeds)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
