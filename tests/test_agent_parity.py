@@ -436,3 +436,45 @@ def test_step_parity_teacher_forced_through_the_dataflow_kernels(dev, name):
         test_step_parity_teacher_forced(dev, name)
     finally:
         dev.lib.b200rl_set_mega(-1)
+
+
+@pytest.mark.parametrize("name", ["td7_halfcheetah_lap", "td3_hopper_uniform", "sac_walker2d"])
+def test_packed_layout_keeps_state_and_action_blocks_16_byte_aligned(dev, name):
+    """A critic's first layer stores [state | pad to 4 | action | pad to 4] (b200rl_agent_layer_split), every other layer one
+    dense block; the engine's state / action input buffers have row strides rounded up to 4 floats (b200rl_agent_io_ld);
+    pack / unpack through the logical column map is the identity, and the padding columns hold zeros."""
+    import ctypes as C
+
+    algo, env_id, prioritized, kwargs, steps = gu.CASES[name]
+    oracle, _, _, _ = gu.make_oracle(name)
+    S, A = oracle.state_dim, oracle.action_dim
+    h = make_c_agent(dev, algo, oracle, kwargs, 0)
+    lds, lda = C.c_int(), C.c_int()
+    dev.check(dev.lib.b200rl_agent_io_ld(h, C.byref(lds), C.byref(lda)))
+    assert lds.value == (S + 3) // 4 * 4 and lda.value == (A + 3) // 4 * 4
+    splits = 0
+    for nid, (nm, layers) in enumerate(net_table(algo)):
+        numel, lay = dev.net_layout(h, nid)
+        for li, (wo, bo, o, n, ld, cols) in enumerate(lay):
+            sp = C.c_int()
+            dev.check(dev.lib.b200rl_agent_layer_split(h, nid, li, C.byref(sp)))
+            is_critic_first = nm in ("q1", "q2", "target_q1", "target_q2", "q1_target", "q2_target") and li == 0
+            if is_critic_first and S % 4:
+                assert sp.value == S and ld == (S + 3) // 4 * 4 + (A + 3) // 4 * 4 and n == S + A
+                splits += 1
+            else:
+                assert sp.value == 0 and ld == (n + 3) // 4 * 4
+            assert wo % 4 == 0 and bo % 4 == 0
+        got = dev.read_net(h, nid)          # logical [out, in] tensors
+        blob = dev.pack_net(h, nid, got)    # back into the padded blob
+        again = dev.unpack_net(h, nid, blob)
+        for (w0, b0), (w1, b1) in zip(got, again):
+            assert np.array_equal(w0, w1) and np.array_equal(b0, b1)
+        for (wo, bo, o, n, ld, cols) in lay:  # padding columns are zero
+            W = blob[wo:wo + o * ld].reshape(o, ld)
+            mask = np.ones(ld, bool)
+            mask[cols] = False
+            assert np.all(W[:, mask] == 0)
+    if S % 4:
+        assert splits >= 2
+    dev.check(dev.lib.b200rl_agent_destroy(h))
