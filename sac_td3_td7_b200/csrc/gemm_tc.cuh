@@ -234,7 +234,7 @@ __device__ __noinline__ void tc_prefetch_epilogue_operands(const GemmProblem& sp
 // access of the epilogue -- C, bias, aux, and Adam's p/m/v -- is a coalesced 128-byte line.
 // Fused AvgL1Norm (act == kActNorm): the warps that share a row group (`nshare` of them, this one is number `qidx`) first
 // add up |x| of their columns straight from TMEM (thread = row), meet at a named barrier, and every thread then knows
-// its row's mean; the second pass is the ordinary transposed write, of x and of x / max(mean|x|, eps).  `nred`:
+// its row's mean; the second pass is the ordinary transposed write, of x and of x * (1 / max(mean|x|, eps)).  `nred`:
 // [2][4][4][32] floats of shared memory (double-buffered by `parity`: a fast warp may start the next tile while a slow one
 // still reads this tile's sums), `ncs`: 32 floats private to the warp.
 template <int MODE>
@@ -265,8 +265,9 @@ __device__ __forceinline__ void tc_epilogue_warp(const GemmProblem& sp, int g, i
     asm volatile("bar.sync %0, %1;" ::"r"(1 + rowgrp), "r"(32 * nshare) : "memory");
     float tot = 0.f;
     for (int q = 0; q < nshare; ++q) tot += slot[q * 32 + lane];
-    ncs[lane] = fmaxf(tot / (float)J, 1e-8f);
-    __syncwarp();
+    ncs[lane] = 1.f / fmaxf(tot / (float)J, 1e-8f);  // the reciprocal, once per row: 64 IEEE divisions per thread in the write pass
+    __syncwarp();                                     // cost as much as the standalone normalisation launches had
+
   }
 #pragma unroll 1
   for (int cc = 0; cc < ncb; ++cc) {
@@ -325,7 +326,7 @@ __device__ __forceinline__ void tc_epilogue_warp(const GemmProblem& sp, int g, i
             for (int u = 0; u < 8; ++u) {
               if (r0 + u < nrows) {
                 cptr[(long long)(r0 + u) * ld] = x[u];
-                yptr[(long long)(r0 + u) * ldy] = x[u] / ncs[r0 + u];
+                yptr[(long long)(r0 + u) * ldy] = x[u] * ncs[r0 + u];
               }
             }
           }
